@@ -1,0 +1,126 @@
+// C-ABI plumbing: error string, device query, and the dense top-k orchestration
+// (candidate selection -> k-way merge -> exact re-score -> optional fp32 re-run of unproven queries).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace drs {
+
+static thread_local std::string g_last_error;
+static thread_local int g_last_dense_kernel = 0;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
+  const bool umma_ok = dense_umma_supported(n_queries, n_rows, dim, kk);
+  if (kernel == DRS_DENSE_UMMA) return umma_ok ? DRS_DENSE_UMMA : -1;
+  if (kernel == DRS_DENSE_SIMT) return DRS_DENSE_SIMT;
+  // AUTO: the streaming fp32 kernel reads the corpus once per 4 queries; beyond 8 queries the
+  // tensor-core kernel (one pass per 128 queries) wins.
+  return (umma_ok && n_queries > 8) ? DRS_DENSE_UMMA : DRS_DENSE_SIMT;
+}
+
+struct DenseWs {
+  size_t parts_keys, cand_keys, flags_off, total;
+  int simt_parts, umma_parts, umma_qstride;
+};
+
+static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
+  DenseWs w{};
+  const size_t kk = cand_len(kprime);
+  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
+  w.simt_parts = dense_simt_grid();
+  w.umma_parts = (which == DRS_DENSE_UMMA) ? dense_umma_parts(n_queries) : 0;
+  w.umma_qstride = ((n_queries + 127) / 128) * 128;
+  const size_t simt_keys = size_t(w.simt_parts) * n_queries * kk;
+  const size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk;
+  w.parts_keys = std::max(simt_keys, umma_keys);
+  w.cand_keys = size_t(n_queries) * kk;
+  w.flags_off = (w.parts_keys + w.cand_keys) * 8;
+  w.total = w.flags_off + size_t(n_queries) * 4 + 256;
+  return w;
+}
+
+}  // namespace drs
+
+using namespace drs;
+
+extern "C" int drs_version(void) { return 100; }
+extern "C" const char* drs_last_error(void) { return g_last_error.c_str(); }
+extern "C" int drs_device_sm_count(void) { return sm_count(); }
+extern "C" int drs_dense_last_kernel(void) { return g_last_dense_kernel; }
+
+extern "C" size_t drs_dense_workspace_bytes(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
+  if (n_queries < 0 || n_rows < 0 || kprime <= 0 || kprime > DRS_MAX_KPRIME) return 0;
+  return dense_ws(n_queries, n_rows, dim, kprime, kernel).total;
+}
+
+extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const void* d_corpus_bf16,
+                              const float* d_inv_norm, const uint8_t* d_row_mask, int64_t n_rows, int dim,
+                              int kprime, int kernel, int escalate, float* d_out_scores, int64_t* d_out_ids,
+                              int32_t* d_out_flags, void* d_workspace, size_t workspace_bytes, void* stream) {
+  DRS_REQUIRE(d_queries_f32 && d_corpus_bf16 && d_inv_norm && d_out_scores && d_out_ids && d_workspace,
+              DRS_ERR_ARG, "dense: null pointer");
+  DRS_REQUIRE(n_queries >= 0 && n_rows > 0 && kprime > 0, DRS_ERR_ARG, "dense: bad sizes");
+  DRS_REQUIRE(kprime <= DRS_MAX_KPRIME, DRS_ERR_UNSUPPORTED, "dense: k' exceeds DRS_MAX_KPRIME");
+  DRS_REQUIRE(dim > 0 && dim % 8 == 0 && dim <= DRS_MAX_DIM, DRS_ERR_UNSUPPORTED,
+              "dense: dim must be a multiple of 8 in (0, 1024]");
+  DRS_REQUIRE(n_rows < (int64_t(1) << 32), DRS_ERR_UNSUPPORTED, "dense: more than 2^32-1 rows in one shard");
+  DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus_bf16) & 15) == 0, DRS_ERR_ARG, "dense: corpus not 16-byte aligned");
+  if (n_queries == 0) return DRS_OK;
+  const int kk = cand_len(kprime);
+  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, kk);
+  DRS_REQUIRE(which > 0, DRS_ERR_UNSUPPORTED, "dense: tensor-core kernel does not support this shape");
+  const DenseWs w = dense_ws(n_queries, n_rows, dim, kprime, kernel);
+  DRS_REQUIRE(workspace_bytes >= w.total, DRS_ERR_WORKSPACE, "dense: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t* parts = reinterpret_cast<uint64_t*>(d_workspace);
+  uint64_t* cand = parts + w.parts_keys;
+  int32_t* flags = d_out_flags ? d_out_flags
+                               : reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.flags_off);
+  g_last_dense_kernel = which;
+  int rc;
+  if (which == DRS_DENSE_SIMT) {
+    rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                           n_queries, nullptr, st);
+    if (rc != DRS_OK) return rc;
+    rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk, cand, nullptr, st);
+    if (rc != DRS_OK) return rc;
+    return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 4e-6f,
+                                d_out_scores, d_out_ids, flags, nullptr, 0, 1, 0, st);
+  }
+  rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                         w.umma_qstride, st);
+  if (rc != DRS_OK) return rc;
+  rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, st);
+  if (rc != DRS_OK) return rc;
+  rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
+                            d_out_scores, d_out_ids, flags, nullptr, 1, 1, 0, st);
+  if (rc != DRS_OK || !escalate) return rc;
+  // Re-run the (few) queries whose tensor-core result is not proven exact through the fp32 kernel.
+  // Everything is predicated on flags[] on the device; with no flagged query the kernels exit at once.
+  rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                         n_queries, flags, st);
+  if (rc != DRS_OK) return rc;
+  rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk, cand, flags, st);
+  if (rc != DRS_OK) return rc;
+  return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 4e-6f,
+                              d_out_scores, d_out_ids, flags, flags, 0, 3, 2, st);
+}

@@ -1,0 +1,255 @@
+// BM25 over a term-major CSR inverted index, document-partitioned into tiles.
+//
+// Stage 1 (bm25_select): HBM-bound.  A CTA owns a run of document tiles.  For one query and one
+// tile it zeroes a shared-memory fp32 score tile, then walks the query's term occurrences IN
+// ORDER; for each it streams the slice of that term's postings that falls inside the tile
+// (coalesced doc-id + impact reads, 8 bytes per posting) and adds the precomputed fp32 impact
+// into the tile.  One barrier per term: inside a term every document appears once, so the adds
+// need no atomics and every document's fp32 sum is formed in the same order => documents that
+// tie exactly in the reference's fp64 arithmetic tie exactly here too.  The tile is then
+// scanned against a running threshold and survivors are merged into the CTA's top-kk list.
+// Tiles and documents are visited in DESCENDING order so that, among equal scores, the larger
+// document id (which the tie rule prefers) is seen first and later equal scores are rejected.
+//
+// Stage 2 (bm25_rescore): the kk surviving candidates per query are re-scored in fp64 with
+// rank_bm25's exact operation order (tf looked up by binary search), sorted by
+// (score desc, doc desc), and the first k' are emitted.
+#include "common.cuh"
+
+namespace drs {
+
+constexpr int BM25_THREADS = 256;
+constexpr int BM25_MBUF = 4096;  // merge buffer (u64 keys): list + candidate append area
+constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
+
+__global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
+    drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
+    int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
+    unsigned long long* __restrict__ gtau) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
+  float* sc = reinterpret_cast<float*>(mbuf + BM25_MBUF);                // [tile_docs]
+  __shared__ int s_cnt;
+  __shared__ unsigned long long s_tau;
+
+  const int T = ix.tile_docs;
+  const int tid = threadIdx.x;
+  const int tile_hi = min(ix.n_tiles, (int(blockIdx.x) + 1) * tiles_per_cta) - 1;
+  const int tile_lo = int(blockIdx.x) * tiles_per_cta;
+  const int cap = BM25_MBUF - kk;
+
+  auto merge = [&](int q) {
+    // callers guarantee all threads arrive here; s_cnt candidates sit at mbuf[kk ..)
+    const int cnt = min(s_cnt, cap);
+    const int n = kk + cnt;
+    const int m = next_pow2(n);
+    for (int i = n + tid; i < m; i += BM25_THREADS) mbuf[i] = 0;
+    __syncthreads();
+    block_bitonic_desc(mbuf, m, [](uint64_t a, uint64_t b) { return a < b; });
+    if (tid == 0) {
+      s_cnt = 0;
+      unsigned long long t = mbuf[kk - 1];  // 0 while the list is not full
+      if (t) atomicMax(gtau + q, t);
+      const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(gtau + q);
+      s_tau = t > g ? t : g;
+    }
+    __syncthreads();
+  };
+
+  for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
+    const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
+    for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
+    if (tid == 0) {
+      s_cnt = 0;
+      s_tau = *reinterpret_cast<volatile unsigned long long*>(gtau + q);
+    }
+    __syncthreads();
+
+    for (int j = tile_hi; j >= tile_lo; --j) {
+      const int64_t doc0 = int64_t(j) * T;
+      const int64_t rem = ix.n_docs - doc0;
+      const int tile_n = rem < int64_t(T) ? int(rem) : T;
+      for (int i = tid; i < T; i += BM25_THREADS) sc[i] = 0.0f;
+      __syncthreads();
+      // ---- accumulate: one term occurrence at a time, in query order -------------------
+      for (int ti = t0; ti < t1; ++ti) {
+        const int t = q_terms[ti];
+        if (t < 0 || t >= ix.n_terms) continue;  // OOV: contributes nothing (block-uniform)
+        const int64_t base = ix.d_term_offsets[t];
+        const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+        const int64_t a = base + tp[0], e = base + tp[1];
+        int64_t p = a + tid;
+        for (; p + 3 * BM25_THREADS < e; p += 4 * BM25_THREADS) {
+          const uint32_t d0 = __ldg(ix.d_post_doc + p), d1 = __ldg(ix.d_post_doc + p + BM25_THREADS);
+          const uint32_t d2 = __ldg(ix.d_post_doc + p + 2 * BM25_THREADS),
+                         d3 = __ldg(ix.d_post_doc + p + 3 * BM25_THREADS);
+          const float i0 = __ldg(ix.d_post_impact + p), i1 = __ldg(ix.d_post_impact + p + BM25_THREADS);
+          const float i2 = __ldg(ix.d_post_impact + p + 2 * BM25_THREADS),
+                      i3 = __ldg(ix.d_post_impact + p + 3 * BM25_THREADS);
+          sc[d0 - doc0] += i0;
+          sc[d1 - doc0] += i1;
+          sc[d2 - doc0] += i2;
+          sc[d3 - doc0] += i3;
+        }
+        for (; p < e; p += BM25_THREADS) sc[__ldg(ix.d_post_doc + p) - doc0] += __ldg(ix.d_post_impact + p);
+        __syncthreads();
+      }
+      // ---- scan the tile, highest document first -----------------------------------------
+      for (int seg = 0; seg < T; seg += BM25_SEG) {
+        const unsigned long long tau = s_tau;
+#pragma unroll
+        for (int u = 0; u < BM25_SEG / BM25_THREADS; ++u) {
+          const int dl = T - 1 - (seg + u * BM25_THREADS + tid);
+          if (dl < tile_n && dl >= 0) {
+            const uint64_t key = make_key(sc[dl], uint32_t(doc0 + dl));
+            if (key > tau) {
+              const int pos = atomicAdd(&s_cnt, 1);
+              if (pos < cap) mbuf[kk + pos] = key;
+            }
+          }
+        }
+        __syncthreads();
+        // merge when the append area could overflow in the next segment, while the list is still
+        // filling (so a threshold exists as early as possible), and at the end of the tile
+        const bool last = (seg + BM25_SEG >= T);
+        const int cnt = s_cnt;
+        if (cnt > 0 && (last || cnt > cap - BM25_SEG || mbuf[kk - 1] == 0)) merge(q);
+      }
+    }
+    for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];
+    __syncthreads();
+  }
+}
+
+// exact fp64 re-scoring of the candidates; rank_bm25 operation order:
+//   score += idf[t] * ( tf*(k1+1) / ( tf + k1*(1-b+b*dl/avgdl) ) )
+__global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, const int32_t* __restrict__ q_terms,
+                                                           const int32_t* __restrict__ q_offsets,
+                                                           const uint64_t* __restrict__ cand, int kk, int kprime,
+                                                           double* __restrict__ out_scores,
+                                                           int64_t* __restrict__ out_ids) {
+  __shared__ uint64_t skey[256];
+  __shared__ int64_t sdoc[256];
+  const int q = blockIdx.x, c = threadIdx.x;
+  const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
+  uint64_t okey = 0;
+  int64_t doc = -1;
+  double score = 0.0;
+  if (c < kk) {
+    const uint64_t key = cand[size_t(q) * kk + c];
+    if (key != 0) {
+      doc = key_row(key);
+      const int j = int(doc / ix.tile_docs);
+      const double kd = ix.d_doc_kd[doc];
+      for (int ti = t0; ti < t1; ++ti) {
+        const int t = q_terms[ti];
+        if (t < 0 || t >= ix.n_terms) continue;
+        const int64_t base = ix.d_term_offsets[t];
+        const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+        int64_t lo = base + tp[0], hi = base + tp[1];  // [lo, hi)
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (ix.d_post_doc[mid] < uint32_t(doc)) lo = mid + 1;
+          else hi = mid;
+        }
+        if (lo < base + tp[1] && ix.d_post_doc[lo] == uint32_t(doc)) {
+          const double tf = double(ix.d_post_tf[lo]);
+          const double num = __dmul_rn(tf, ix.k1_plus_1);
+          const double den = __dadd_rn(tf, kd);
+          score = __dadd_rn(score, __dmul_rn(ix.d_idf[t], __ddiv_rn(num, den)));
+        }
+      }
+      okey = ord64(score);
+    }
+  }
+  skey[c] = okey;
+  sdoc[c] = doc;
+  __syncthreads();
+  if (c < kk && doc >= 0) {
+    int rank = 0;
+    for (int o = 0; o < kk; ++o) {
+      const int64_t od = sdoc[o];
+      if (od < 0) continue;
+      const uint64_t ok = skey[o];
+      rank += (ok > okey) || (ok == okey && od > doc);
+    }
+    if (rank < kprime) {
+      out_scores[size_t(q) * kprime + rank] = score;
+      out_ids[size_t(q) * kprime + rank] = doc;
+    }
+  }
+  // pad the tail when fewer than k' candidates exist
+  __shared__ int s_valid;
+  if (c == 0) s_valid = 0;
+  __syncthreads();
+  if (c < kk && doc >= 0) atomicAdd(&s_valid, 1);
+  __syncthreads();
+  for (int i = s_valid + c; i < kprime; i += blockDim.x) {
+    out_scores[size_t(q) * kprime + i] = -INFINITY;
+    out_ids[size_t(q) * kprime + i] = -1;
+  }
+}
+
+static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& gy, int& tiles_per_cta) {
+  const int target = 4 * sm_count();
+  gx = ix->n_tiles < target ? ix->n_tiles : target;
+  if (gx < 1) gx = 1;
+  tiles_per_cta = (ix->n_tiles + gx - 1) / gx;
+  if (tiles_per_cta < 1) tiles_per_cta = 1;
+  gx = (ix->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+  if (gx < 1) gx = 1;
+  gy = (target + gx - 1) / gx;
+  if (gy > n_queries) gy = n_queries;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+}
+
+}  // namespace drs
+
+using namespace drs;
+
+extern "C" size_t drs_bm25_workspace_bytes(int n_queries, const drs_bm25_index* index, int kprime) {
+  if (!index || n_queries < 0 || kprime <= 0) return 0;
+  int gx, gy, tpc;
+  bm25_grid(index, n_queries > 0 ? n_queries : 1, gx, gy, tpc);
+  const size_t kk = cand_len(kprime);
+  size_t b = size_t(gx) * n_queries * kk * 8;  // partial lists
+  b += size_t(n_queries) * kk * 8;             // merged candidates
+  b += size_t(n_queries) * 8;                  // shared thresholds
+  return b + 256;
+}
+
+extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
+                             int n_queries, int kprime, double* d_out_scores, int64_t* d_out_ids,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+  DRS_REQUIRE(index && d_q_offsets && d_out_scores && d_out_ids && d_workspace, DRS_ERR_ARG, "bm25: null pointer");
+  DRS_REQUIRE(n_queries >= 0 && kprime > 0, DRS_ERR_ARG, "bm25: bad sizes");
+  DRS_REQUIRE(kprime <= DRS_MAX_KPRIME, DRS_ERR_UNSUPPORTED, "bm25: k' exceeds DRS_MAX_KPRIME");
+  const drs_bm25_index& ix = *index;
+  DRS_REQUIRE(ix.n_docs > 0 && ix.n_docs < (int64_t(1) << 32), DRS_ERR_UNSUPPORTED, "bm25: n_docs out of range");
+  DRS_REQUIRE(ix.tile_docs >= 256 && ix.tile_docs <= 8192 && (ix.tile_docs & (ix.tile_docs - 1)) == 0,
+              DRS_ERR_UNSUPPORTED, "bm25: tile_docs must be a power of two in [256, 8192]");
+  DRS_REQUIRE(ix.n_tiles == int((ix.n_docs + ix.tile_docs - 1) / ix.tile_docs), DRS_ERR_ARG, "bm25: n_tiles mismatch");
+  DRS_REQUIRE(workspace_bytes >= drs_bm25_workspace_bytes(n_queries, index, kprime), DRS_ERR_WORKSPACE,
+              "bm25: workspace too small");
+  if (n_queries == 0) return DRS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int kk = cand_len(kprime);
+  int gx, gy, tpc;
+  bm25_grid(index, n_queries, gx, gy, tpc);
+  uint64_t* parts = reinterpret_cast<uint64_t*>(d_workspace);
+  uint64_t* cand = parts + size_t(gx) * n_queries * kk;
+  unsigned long long* gtau = reinterpret_cast<unsigned long long*>(cand + size_t(n_queries) * kk);
+  DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8, st));
+  const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
+  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  bm25_select_kernel<<<dim3(gx, gy), BM25_THREADS, smem, st>>>(ix, d_q_terms, d_q_offsets, n_queries, kk, tpc,
+                                                               parts, n_queries, gtau);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  int rc = launch_merge_keys(parts, gx, n_queries, n_queries, kk, cand, nullptr, st);
+  if (rc != DRS_OK) return rc;
+  bm25_rescore_kernel<<<n_queries, 256, 0, st>>>(ix, d_q_terms, d_q_offsets, cand, kk, kprime, d_out_scores,
+                                                 d_out_ids);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}

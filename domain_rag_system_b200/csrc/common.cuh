@@ -1,0 +1,125 @@
+// Shared device/host helpers for the hybrid-retrieval kernels (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstring>
+#include <string>
+
+#include "../../include/drs_b200.h"
+
+namespace drs {
+
+// ---- error plumbing (thread-local message, C ABI returns codes) --------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define DRS_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return ::drs::fail(DRS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+#define DRS_REQUIRE(cond, code, msg) \
+  do {                               \
+    if (!(cond)) return ::drs::fail((code), (msg)); \
+  } while (0)
+
+int sm_count();
+
+// ---- sortable keys -------------------------------------------------------------------
+// A candidate is (score, row).  Order everywhere: score descending, then row descending
+// (the determinised `np.argsort(scores)[::-1]`).  Packing the order-preserving image of
+// the fp32 score above the row gives a u64 whose plain integer order is that order.
+// Key 0 is "empty slot" (no finite or infinite score maps to 0).
+__host__ __device__ __forceinline__ uint32_t ord32(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f + 0.0f);  // -0.0 -> +0.0 so the two zeros tie
+#else
+  float g = f + 0.0f;
+  uint32_t u;
+  memcpy(&u, &g, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float unord32(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  return (uint64_t(ord32(score)) << 32) | row;
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t k) { return unord32(uint32_t(k >> 32)); }
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return uint32_t(k); }
+
+__device__ __forceinline__ uint64_t ord64(double d) {
+  uint64_t u = (uint64_t)__double_as_longlong(d + 0.0);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// ---- block-wide bitonic sort, descending, n a power of two, data in shared memory -------
+template <typename T, typename Less>
+__device__ __forceinline__ void block_bitonic_desc(T* s, int n, Less less) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          T a = s[i], b = s[ixj];
+          bool desc = ((i & k) == 0);
+          // descending block: larger first
+          if (desc ? less(a, b) : less(b, a)) {
+            s[i] = b;
+            s[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__host__ __device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// candidate-list length carried through the approximate stages: k' plus a margin that the
+// exact re-scoring stage consumes (see DESIGN.md "exactness").
+__host__ __device__ __forceinline__ int cand_len(int kprime) { return kprime + 8 + (kprime >> 2); }
+
+// ---- launchers implemented in the .cu files ---------------------------------------------
+// select.cu
+int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
+                      uint64_t* d_out, const int32_t* d_active, cudaStream_t st);
+int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                         int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
+                         float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
+                         const int32_t* d_active, int query_rounded_bf16, int flag_unproven, int flag_proven,
+                         cudaStream_t st);
+// dense_simt.cu
+int dense_simt_grid();
+int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
+                      int q_stride, const int32_t* d_active, cudaStream_t st);
+// dense_umma.cu
+bool dense_umma_supported(int n_queries, int64_t n_rows, int dim, int kk);
+int dense_umma_parts(int n_queries);
+int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
+                      int q_stride, cudaStream_t st);
+
+}  // namespace drs

@@ -1,0 +1,269 @@
+// Candidate-list kernels: k-way merge of partial top-k lists, exact re-scoring of dense
+// candidates, and the C-ABI merge used after the multi-GPU all-gather.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace drs {
+
+// ------------------------------------------------------------------------------------------
+// merge_keys: one CTA per query.  Input: n_parts lists of kk u64 keys each (unsorted, 0 =
+// empty), laid out parts[(p * q_stride + q) * kk + c].  Output: the kk largest keys,
+// descending.  Chunked block bitonic sort so any n_parts works.
+// ------------------------------------------------------------------------------------------
+constexpr int MERGE_BUF = 2048;
+
+__global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restrict__ parts, int n_parts,
+                                                         int q_stride, int kk, uint64_t* __restrict__ out,
+                                                         const int32_t* __restrict__ active) {
+  __shared__ uint64_t buf[MERGE_BUF];
+  const int q = blockIdx.x;
+  if (active != nullptr && active[q] == 0) return;
+  const int n = n_parts * kk;
+  for (int i = threadIdx.x; i < kk; i += blockDim.x) buf[i] = 0;
+  int pos = 0;
+  while (pos < n) {
+    const int take = min(MERGE_BUF - kk, n - pos);
+    const int m = next_pow2(kk + take);
+    for (int i = threadIdx.x; i < m - kk; i += blockDim.x) {
+      uint64_t v = 0;
+      if (i < take) {
+        const int f = pos + i;
+        const int p = f / kk, c = f - p * kk;
+        v = parts[(size_t(p) * q_stride + q) * kk + c];
+      }
+      buf[kk + i] = v;
+    }
+    __syncthreads();
+    block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
+    pos += take;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kk; i += blockDim.x) out[size_t(q) * kk + i] = buf[i];
+}
+
+int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
+                      uint64_t* d_out, const int32_t* d_active, cudaStream_t st) {
+  DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2, DRS_ERR_UNSUPPORTED, "merge: list length out of range");
+  merge_keys_kernel<<<n_queries, 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_out, d_active);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dense_rescore: exact cosine of the kk surviving candidates of each query.
+// score = fp32( dot_fp64(q_fp32, row_bf16) * (1/||q||) * inv_norm[row] ), i.e. the reference's
+// renormalise-then-dot (qdrant local mode) with the dot product carried in fp64.
+// Then sort by (score desc, row desc) and emit the first k'.
+// Flag: the selection stages ranked rows by an APPROXIMATE score whose error is bounded by
+// approx_err (in normalised-score units).  Every row outside the candidate list has
+// approximate score <= the list's smallest; if that plus the bound is still below the exact
+// k'-th score, no outside row can belong to the top-k' => proven exact (flag 0), else flag 1.
+// ------------------------------------------------------------------------------------------
+constexpr int RESCORE_MAXC = 256;
+
+__global__ void __launch_bounds__(256) dense_rescore_kernel(
+    const float* __restrict__ queries, const __nv_bfloat16* __restrict__ corpus,
+    const float* __restrict__ inv_norm, int dim, const uint64_t* __restrict__ cand, int kk, int kprime,
+    float approx_err, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
+    int32_t* __restrict__ flags, const int32_t* __restrict__ active, int query_rounded_bf16,
+    int flag_value_unproven, int flag_value_proven) {
+  __shared__ float sq[DRS_MAX_DIM];
+  __shared__ uint64_t ekey[RESCORE_MAXC];
+  __shared__ double red[8];
+  __shared__ double red2[8];
+  __shared__ float s_amin;
+  __shared__ int s_nvalid;
+  const int q = blockIdx.x;
+  if (active != nullptr && active[q] == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // query -> smem, ||q||^2 and ||q - bf16(q)||^2 in fp64
+  double part = 0.0, perr = 0.0;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    float v = queries[size_t(q) * dim + i];
+    sq[i] = v;
+    part += double(v) * double(v);
+    const double d = double(v) - double(__bfloat162float(__float2bfloat16_rn(v)));
+    perr += d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    part += __shfl_xor_sync(0xffffffffu, part, o);
+    perr += __shfl_xor_sync(0xffffffffu, perr, o);
+  }
+  if (lane == 0) {
+    red[warp] = part;
+    red2[warp] = perr;
+  }
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  double qn2 = 0.0, qe2 = 0.0;
+  for (int w = 0; w < 8; ++w) {
+    qn2 += red[w];
+    qe2 += red2[w];
+  }
+  const double inv_q = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
+  // Cauchy-Schwarz: |(q - bf16(q)) . c| * inv_norm[c] * inv_q <= ||q - bf16(q)|| * inv_q  (||c||*inv_norm = 1)
+  const float err_bound = approx_err + (query_rounded_bf16 ? float(sqrt(qe2) * inv_q * 1.0001) : 0.0f);
+
+  const int m = next_pow2(kk);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) ekey[i] = 0;
+  __syncthreads();
+
+  float amin = INFINITY;
+  int nvalid = 0;
+  for (int c = warp; c < kk; c += 8) {
+    const uint64_t key = cand[size_t(q) * kk + c];
+    if (key == 0) continue;
+    const uint32_t row = key_row(key);
+    const uint4* rp = reinterpret_cast<const uint4*>(corpus + size_t(row) * dim);
+    double acc = 0.0;
+    for (int e = lane * 8; e < dim; e += 256) {
+      const uint4 w = __ldg(rp + (e >> 3));
+      const float* qq = sq + e;
+      acc += double(bf16_lo(w.x)) * double(qq[0]);
+      acc += double(bf16_hi(w.x)) * double(qq[1]);
+      acc += double(bf16_lo(w.y)) * double(qq[2]);
+      acc += double(bf16_hi(w.y)) * double(qq[3]);
+      acc += double(bf16_lo(w.z)) * double(qq[4]);
+      acc += double(bf16_hi(w.z)) * double(qq[5]);
+      acc += double(bf16_lo(w.w)) * double(qq[6]);
+      acc += double(bf16_hi(w.w)) * double(qq[7]);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float s = float(acc * inv_q * double(inv_norm[row]));
+      ekey[c] = make_key(s, row);
+      amin = fminf(amin, key_score(key));
+      ++nvalid;
+    }
+  }
+  if (lane == 0) atomicAdd(&s_nvalid, nvalid);
+  __shared__ float wmin[8];
+  if (lane == 0) wmin[warp] = amin;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = INFINITY;
+    for (int w = 0; w < 8; ++w) a = fminf(a, wmin[w]);
+    s_amin = a;
+  }
+  __syncthreads();
+  block_bitonic_desc(ekey, m, [](uint64_t a, uint64_t b) { return a < b; });
+
+  for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
+    const uint64_t k = (i < m) ? ekey[i] : 0;
+    out_scores[size_t(q) * kprime + i] = k ? key_score(k) : -INFINITY;
+    out_ids[size_t(q) * kprime + i] = k ? int64_t(key_row(k)) : int64_t(-1);
+  }
+  if (threadIdx.x == 0 && flags != nullptr) {
+    int f = flag_value_proven;
+    if (s_nvalid >= kk && kprime <= kk) {  // list was full: rows outside it exist
+      const float tau = key_score(ekey[kprime - 1]);
+      const float outside_best = float(double(s_amin) * inv_q) + err_bound;
+      f = (outside_best < tau) ? 0 : flag_value_unproven;
+    }
+    flags[q] = f;
+  }
+}
+
+int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                         int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
+                         float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
+                         const int32_t* d_active, int query_rounded_bf16, int flag_unproven, int flag_proven,
+                         cudaStream_t st) {
+  DRS_REQUIRE(kk <= RESCORE_MAXC, DRS_ERR_UNSUPPORTED, "rescore: candidate list too long");
+  dense_rescore_kernel<<<n_queries, 256, 0, st>>>(d_q, reinterpret_cast<const __nv_bfloat16*>(d_corpus),
+                                                   d_inv_norm, dim, d_cand, kk, kprime, approx_err,
+                                                   d_out_scores, d_out_ids, d_flags, d_active,
+                                                   query_rounded_bf16, flag_unproven, flag_proven);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// C-ABI merges (post all-gather).  (score, id) pairs, order (score desc, id desc).
+// ------------------------------------------------------------------------------------------
+struct Pair64 {
+  uint64_t s;  // ordered image of the score
+  int64_t id;  // -1 = absent
+};
+__device__ __forceinline__ bool pair_less(const Pair64& a, const Pair64& b) {
+  return (a.s < b.s) || (a.s == b.s && a.id < b.id);
+}
+
+template <typename ScoreT>
+__global__ void __launch_bounds__(256) merge_pairs_kernel(const ScoreT* __restrict__ scores,
+                                                          const int64_t* __restrict__ ids, int n_parts,
+                                                          int n_queries, int k, int k_out,
+                                                          ScoreT* __restrict__ out_scores,
+                                                          int64_t* __restrict__ out_ids) {
+  constexpr int BUF = 1024;
+  __shared__ Pair64 buf[BUF];
+  const int q = blockIdx.x;
+  const int n = n_parts * k;
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) buf[i] = Pair64{0, -1};
+  int pos = 0;
+  while (pos < n) {
+    const int take = min(BUF - k_out, n - pos);
+    const int m = next_pow2(k_out + take);
+    for (int i = threadIdx.x; i < m - k_out; i += blockDim.x) {
+      Pair64 v{0, -1};
+      if (i < take) {
+        const int f = pos + i;
+        const int p = f / k, c = f - p * k;
+        const size_t at = (size_t(p) * n_queries + q) * k + c;
+        const int64_t id = ids[at];
+        if (id >= 0) {
+          if constexpr (sizeof(ScoreT) == 4) v.s = uint64_t(ord32(float(scores[at]))) << 32;
+          else v.s = ord64(double(scores[at]));
+          v.id = id;
+        }
+      }
+      buf[k_out + i] = v;
+    }
+    __syncthreads();
+    block_bitonic_desc(buf, m, pair_less);
+    pos += take;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+    const Pair64 v = buf[i];
+    ScoreT s;
+    if (v.id < 0) s = ScoreT(-INFINITY);
+    else if constexpr (sizeof(ScoreT) == 4) s = ScoreT(unord32(uint32_t(v.s >> 32)));
+    else {
+      const uint64_t u = (v.s >> 63) ? (v.s & 0x7fffffffffffffffull) : ~v.s;
+      s = ScoreT(__longlong_as_double((long long)u));
+    }
+    out_scores[size_t(q) * k_out + i] = s;
+    out_ids[size_t(q) * k_out + i] = v.id;
+  }
+}
+
+template <typename ScoreT>
+static int merge_pairs(const ScoreT* d_scores, const int64_t* d_ids, int n_parts, int n_queries, int k,
+                       int k_out, ScoreT* d_out_scores, int64_t* d_out_ids, void* stream) {
+  DRS_REQUIRE(d_scores && d_ids && d_out_scores && d_out_ids, DRS_ERR_ARG, "merge: null pointer");
+  DRS_REQUIRE(n_parts > 0 && n_queries >= 0 && k > 0 && k_out > 0, DRS_ERR_ARG, "merge: bad sizes");
+  DRS_REQUIRE(k_out <= 512, DRS_ERR_UNSUPPORTED, "merge: k_out > 512");
+  if (n_queries == 0) return DRS_OK;
+  merge_pairs_kernel<ScoreT><<<n_queries, 256, 0, (cudaStream_t)stream>>>(
+      d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}
+
+}  // namespace drs
+
+extern "C" int drs_merge_candidates_f32(const float* d_scores, const int64_t* d_ids, int n_parts,
+                                        int n_queries, int k, int k_out, float* d_out_scores,
+                                        int64_t* d_out_ids, void* stream) {
+  return drs::merge_pairs<float>(d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids,
+                                 stream);
+}
+extern "C" int drs_merge_candidates_f64(const double* d_scores, const int64_t* d_ids, int n_parts,
+                                        int n_queries, int k, int k_out, double* d_out_scores,
+                                        int64_t* d_out_ids, void* stream) {
+  return drs::merge_pairs<double>(d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids,
+                                  stream);
+}

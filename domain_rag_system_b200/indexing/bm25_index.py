@@ -1,0 +1,236 @@
+"""Device-resident BM25 index: term-major CSR postings + per-tile offsets.
+
+Host/torch-side construction of what ``rank_bm25.BM25Okapi.__init__`` builds (called at
+reference ``src/indexing/bm25_indexer.py:102-106``), laid out for the CUDA kernels in
+``csrc/bm25.cu`` (see ``include/drs_b200.h: drs_bm25_index``):
+
+* ``idf[t] = ln(N - df + 0.5) - ln(df + 0.5)`` (``math.log``), summed in the library's
+  dict-insertion order (first appearance of the term in the token stream) to get
+  ``average_idf``; negative idfs are replaced by ``epsilon * average_idf``;
+* ``doc_kd[d] = k1 * (1 - b + b * doc_len[d] / avgdl)`` in fp64, same operation order;
+* postings sorted by (term, doc): ``post_doc`` u32, ``post_tf`` u16,
+  ``post_impact`` = fp32(idf * tf*(k1+1) / (tf + doc_kd[doc]));
+* ``tile_ptr[t, j]`` = first posting of term t whose doc >= j*tile_docs (relative).
+
+The construction uses torch ops so it runs on the GPU for large corpora (sort-based CSR
+build) and on the CPU in unit tests; only the V-long idf loop is Python.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+def choose_tile_docs(n_docs: int, sm_count: int = 148) -> int:
+    t = 256
+    while t < 8192 and n_docs // t > 4 * sm_count:
+        t *= 2
+    return t
+
+
+class Bm25DeviceIndex:
+    def __init__(self):
+        self.n_docs = 0
+        self.n_terms = 0
+        self.tile_docs = 0
+        self.n_tiles = 0
+        self.k1 = 1.5
+        self.b = 0.75
+        self.epsilon = 0.25
+        self.avgdl = 0.0
+        self.average_idf = 0.0
+        self.vocab: Dict[str, int] | None = None   # term string -> id (None for id-only corpora)
+        self.vocab_present = 0                     # number of distinct terms that occur
+        self.total_tokens = 0
+        self.t: Dict[str, torch.Tensor] = {}       # device tensors
+        self._struct = None
+
+    # rank_bm25-style attribute names, used by get_stats / tests
+    @property
+    def corpus_size(self):
+        return self.n_docs
+
+    # -----------------------------------------------------------------------------
+    @classmethod
+    def from_token_ids(cls, doc_offsets, tokens, vocab_size: int, k1=1.5, b=0.75, epsilon=0.25,
+                       device="cuda", tile_docs: int | None = None, build_device=None):
+        """``doc_offsets`` int64 [N+1], ``tokens`` int32 [total] (term ids in [0, vocab_size))."""
+        self = cls()
+        build_device = torch.device(build_device or device)
+        device = torch.device(device)
+        offs = torch.as_tensor(np.asarray(doc_offsets), dtype=torch.int64)
+        n = int(offs.numel() - 1)
+        if n <= 0:
+            raise ValueError("empty corpus")  # rank_bm25 divides by corpus_size
+        total = int(offs[-1])
+        self.n_docs, self.n_terms, self.k1, self.b, self.epsilon = n, int(vocab_size), k1, b, epsilon
+        self.total_tokens = total
+        self.avgdl = total / n
+        doc_len = (offs[1:] - offs[:-1]).to(build_device)
+        toks = torch.as_tensor(np.asarray(tokens)).to(build_device, dtype=torch.int64)
+        doc_of_tok = torch.repeat_interleave(torch.arange(n, device=build_device, dtype=torch.int64), doc_len)
+        # (term, doc) pairs -> sorted unique with counts == postings with tf
+        ukey, tf = torch.unique(toks * n + doc_of_tok, return_counts=True)
+        del doc_of_tok
+        post_term = torch.div(ukey, n, rounding_mode="floor")
+        post_doc = ukey - post_term * n
+        del ukey
+        df = torch.bincount(post_term, minlength=self.n_terms)
+        term_offsets = torch.zeros(self.n_terms + 1, dtype=torch.int64, device=build_device)
+        term_offsets[1:] = torch.cumsum(df, 0)
+        # idf in dict-insertion order (first appearance in the token stream)
+        first_pos = torch.full((self.n_terms,), total, dtype=torch.int64, device=build_device)
+        if total:
+            first_pos.scatter_reduce_(0, toks, torch.arange(total, device=build_device, dtype=torch.int64),
+                                      reduce="amin", include_self=True)
+        del toks
+        df_h = df.cpu().numpy()
+        order = np.argsort(first_pos.cpu().numpy(), kind="stable")
+        idf = np.zeros(self.n_terms, dtype=np.float64)
+        idf_sum = 0
+        neg = []
+        present = 0
+        for t in order:
+            d = int(df_h[t])
+            if d == 0:
+                continue
+            v = math.log(n - d + 0.5) - math.log(d + 0.5)
+            idf[t] = v
+            idf_sum += v
+            present += 1
+            if v < 0:
+                neg.append(t)
+        if present == 0:
+            raise ValueError("corpus has no tokens")  # rank_bm25: division by zero in average_idf
+        self.vocab_present = present
+        self.average_idf = idf_sum / present
+        if neg:
+            idf[np.array(neg, dtype=np.int64)] = self.epsilon * self.average_idf
+        # per-document length normaliser, fp64, reference operation order
+        dl_h = doc_len.cpu().numpy()
+        kd_h = self.k1 * (1 - self.b + self.b * dl_h / self.avgdl)
+        kd = torch.from_numpy(kd_h).to(build_device)
+        idf_d = torch.from_numpy(idf).to(build_device)
+        tf64 = tf.to(torch.float64)
+        impact = (idf_d[post_term] * (tf64 * (self.k1 + 1) / (tf64 + kd[post_doc]))).to(torch.float32)
+        if int(tf.max()) > 65535:
+            raise NotImplementedError("term frequency above 65535 in one chunk")
+        # per-tile offsets
+        self.tile_docs = int(tile_docs or choose_tile_docs(n))
+        self.n_tiles = (n + self.tile_docs - 1) // self.tile_docs
+        shift = int(math.log2(self.tile_docs))
+        cell = post_term * self.n_tiles + (post_doc >> shift)
+        cnt = torch.bincount(cell, minlength=self.n_terms * self.n_tiles).view(self.n_terms, self.n_tiles)
+        del cell
+        tile_ptr = torch.zeros(self.n_terms, self.n_tiles + 1, dtype=torch.int64, device=build_device)
+        torch.cumsum(cnt, 1, out=tile_ptr[:, 1:])
+        del cnt
+        self.t = {
+            "term_offsets": term_offsets.to(device),
+            "post_doc": post_doc.to(torch.int32).to(device),      # bit pattern of u32 (n < 2^31 enforced below)
+            "post_impact": impact.to(device),
+            "post_tf": tf.to(torch.int16).to(device),             # bit pattern of u16
+            "tile_ptr": tile_ptr.to(torch.int32).contiguous().to(device),
+            "idf": idf_d.to(device),
+            "doc_kd": kd.to(device),
+            "doc_len": doc_len.to(torch.int32).to(device),
+        }
+        if n >= (1 << 31):
+            raise NotImplementedError("more than 2^31-1 documents in one shard")
+        self._struct = None
+        return self
+
+    @classmethod
+    def from_token_lists(cls, tokenized_corpus: Sequence[Sequence[str]], k1=1.5, b=0.75, epsilon=0.25,
+                         device="cuda", tile_docs=None, build_device=None):
+        """The drop-in path: documents are lists of token strings."""
+        vocab: Dict[str, int] = {}
+        lens = np.fromiter((len(d) for d in tokenized_corpus), dtype=np.int64, count=len(tokenized_corpus))
+        offs = np.zeros(len(tokenized_corpus) + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        toks = np.empty(int(offs[-1]), dtype=np.int32)
+        p = 0
+        for doc in tokenized_corpus:
+            for w in doc:
+                i = vocab.get(w)
+                if i is None:
+                    i = vocab[w] = len(vocab)
+                toks[p] = i
+                p += 1
+        self = cls.from_token_ids(offs, toks, max(len(vocab), 1), k1, b, epsilon, device, tile_docs, build_device)
+        self.vocab = vocab
+        return self
+
+    # -----------------------------------------------------------------------------
+    def struct(self) -> _lib.Bm25IndexStruct:
+        if self._struct is None:
+            s = _lib.Bm25IndexStruct()
+            s.n_docs, s.n_terms, s.tile_docs, s.n_tiles, s.reserved = (self.n_docs, self.n_terms, self.tile_docs,
+                                                                       self.n_tiles, 0)
+            t = self.t
+            s.d_term_offsets = t["term_offsets"].data_ptr()
+            s.d_post_doc = t["post_doc"].data_ptr()
+            s.d_post_impact = t["post_impact"].data_ptr()
+            s.d_post_tf = t["post_tf"].data_ptr()
+            s.d_tile_ptr = t["tile_ptr"].data_ptr()
+            s.d_idf = t["idf"].data_ptr()
+            s.d_doc_kd = t["doc_kd"].data_ptr()
+            s.k1_plus_1 = self.k1 + 1
+            self._struct = s
+        return self._struct
+
+    @property
+    def device(self):
+        return self.t["post_doc"].device
+
+    @property
+    def nnz(self):
+        return int(self.t["post_doc"].numel())
+
+    def encode_queries(self, queries: Sequence[Sequence], pinned: bool = False):
+        """Token strings (or term ids) -> (q_terms int32, q_offsets int32) HOST tensors.
+        Unknown strings become -1 (``idf.get(q) or 0`` in rank_bm25 => no contribution)."""
+        offs = np.zeros(len(queries) + 1, dtype=np.int32)
+        flat: List[int] = []
+        for i, q in enumerate(queries):
+            for w in q:
+                if isinstance(w, str):
+                    flat.append(self.vocab.get(w, -1) if self.vocab is not None else -1)
+                else:
+                    w = int(w)
+                    flat.append(w if 0 <= w < self.n_terms else -1)
+            offs[i + 1] = len(flat)
+        qt = torch.from_numpy(np.asarray(flat, dtype=np.int32).reshape(-1))
+        qo = torch.from_numpy(offs)
+        if pinned:
+            qt, qo = qt.pin_memory(), qo.pin_memory()
+        return qt, qo
+
+    def df_of(self, term_ids) -> np.ndarray:
+        to = self.t["term_offsets"]
+        ids = torch.as_tensor(np.asarray(term_ids, dtype=np.int64), device=to.device)
+        ok = (ids >= 0) & (ids < self.n_terms)
+        ids = ids.clamp(0, self.n_terms - 1)
+        return ((to[ids + 1] - to[ids]) * ok).cpu().numpy()
+
+    # -- persistence (our own format; tensors moved to the host) ---------------------
+    def state_dict(self):
+        return {"meta": dict(n_docs=self.n_docs, n_terms=self.n_terms, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
+                             k1=self.k1, b=self.b, epsilon=self.epsilon, avgdl=self.avgdl,
+                             average_idf=self.average_idf, vocab_present=self.vocab_present,
+                             total_tokens=self.total_tokens),
+                "vocab": self.vocab, "tensors": {k: v.cpu() for k, v in self.t.items()}}
+
+    @classmethod
+    def from_state_dict(cls, sd, device="cuda"):
+        self = cls()
+        for k, v in sd["meta"].items():
+            setattr(self, k, v)
+        self.vocab = sd["vocab"]
+        self.t = {k: v.to(device) for k, v in sd["tensors"].items()}
+        return self

@@ -1,0 +1,206 @@
+"""Drop-in ``VectorIndexer`` (reference ``src/indexing/vector_indexer.py``) on the CUDA path.
+
+The embedded Qdrant collection becomes a bf16 row-major matrix in HBM plus fp32 inverse
+row norms; ``query_points`` becomes ``drs_dense_topk``.  Payload dicts stay on the host,
+indexed by row (the reference's point id == row index, vector_indexer.py:133-135).
+"""
+from __future__ import annotations
+
+import json
+import pickle
+import weakref
+from pathlib import Path
+from typing import Dict, List
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .bm25_indexer import chunk_as_dict
+
+# embedder object -> VectorIndexer holding the rows that embedder produced.  Lets the simple
+# reranker (which only receives the embedder, scripts/query.py:153-158) find stored rows
+# instead of re-embedding texts.
+_BY_EMBEDDER: "weakref.WeakValueDictionary[int, VectorIndexer]" = weakref.WeakValueDictionary()
+
+
+def indexer_for_embedder(embedder):
+    return _BY_EMBEDDER.get(id(embedder))
+
+
+class VectorIndexer:
+    def __init__(self, collection_name: str = "medical_docs", embedder=None, storage_path: str = "./data/vector_db",
+                 distance_metric: str = "cosine", use_in_memory: bool = False, device=None):
+        _lib.load()  # ImportError when the CUDA library is missing (reference: qdrant-client missing, :44-45)
+        if embedder is None:
+            raise ValueError("an embedder object is required (model inference is outside this package); "
+                             "pass the reference's MedicalEmbedder or a TableEmbedder")
+        self.collection_name = collection_name
+        self.embedder = embedder
+        self.use_in_memory = use_in_memory
+        if not use_in_memory:
+            self.storage_path = Path(storage_path)
+            self.storage_path.mkdir(parents=True, exist_ok=True)
+        else:
+            self.storage_path = None
+        metric = distance_metric.lower()
+        self.distance_metric = metric if metric in ("cosine", "euclidean", "dot") else "cosine"
+        if self.distance_metric != "cosine":
+            raise NotImplementedError("only distance_metric='cosine' is built (SURVEY.md 8f row 3)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.rows: torch.Tensor | None = None        # bf16 [N, D] in HBM
+        self.inv_norm: torch.Tensor | None = None    # fp32 [N]
+        self.payloads: List[Dict] = []
+        self._exists = False
+        self._ws = _lib.Workspace()
+        self._mask_cache: Dict = {}
+        self._text_rows: Dict[str, int] | None = None
+        _BY_EMBEDDER[id(embedder)] = self
+        if use_in_memory:
+            print("Initialized in-memory vector store")
+        else:
+            print(f"Initialized persistent vector store at: {self.storage_path}")
+            self._try_attach()
+        print(f"Collection: {collection_name}")
+        print(f"Embedding model: {self.embedder.model_name}")
+
+    # -- persistence: <storage>/collection/<name>/{rows.pt,payload.pkl} ----------------------
+    def _dir(self) -> Path:
+        return self.storage_path / "collection" / self.collection_name
+
+    def _try_attach(self):
+        d = self._dir()
+        if (d / "rows.pt").exists():
+            self.set_rows(torch.load(d / "rows.pt", map_location="cpu"))
+            with open(d / "payload.pkl", "rb") as f:
+                self.payloads = pickle.load(f)
+            self._exists = True
+
+    def _persist(self):
+        if self.storage_path is None or self.rows is None:
+            return
+        d = self._dir()
+        d.mkdir(parents=True, exist_ok=True)
+        torch.save(self.rows.cpu(), d / "rows.pt")
+        with open(d / "payload.pkl", "wb") as f:
+            pickle.dump(self.payloads, f)
+        with open(self.storage_path / "meta.json", "w") as f:
+            json.dump({"collections": {self.collection_name: {"size": int(self.rows.shape[1]),
+                                                              "distance": self.distance_metric}}}, f)
+
+    # -- vector_indexer.py:74-103 ------------------------------------------------------------
+    def create_collection(self, force_recreate: bool = True):
+        if self._exists and force_recreate:
+            print(f"Deleting existing collection: {self.collection_name}")
+            self.delete_collection(_quiet=True)
+        if not self._exists:
+            print(f"Creating collection: {self.collection_name}")
+            self.rows, self.inv_norm, self.payloads = None, None, []
+            self._exists = True
+            print(f"Collection created with dimension: {self.embedder.embedding_dim}")
+        else:
+            print(f"Collection {self.collection_name} already exists")
+
+    def set_rows(self, rows):
+        """Install the corpus matrix: any float tensor/array [N, D] -> bf16 in HBM + inverse norms."""
+        t = torch.as_tensor(rows)
+        t = t.to(self.device, non_blocking=True)
+        if t.dtype != torch.bfloat16:
+            t = t.to(torch.bfloat16)
+        self.rows = t.contiguous()
+        self.inv_norm = _lib.row_inv_norms(self.rows)
+        self._mask_cache.clear()
+        self._text_rows = None
+
+    # -- vector_indexer.py:105-163 -----------------------------------------------------------
+    def index_chunks(self, chunks: List, batch_size: int = 100):
+        print(f"\nIndexing {len(chunks)} chunks...")
+        if not self._exists:
+            raise RuntimeError(f"Collection {self.collection_name} does not exist")  # qdrant raises on upsert
+        texts = [c.text if hasattr(c, "text") else c["text"] for c in chunks]
+        print("Generating embeddings...")
+        emb = np.asarray(self.embedder.encode(texts), dtype=np.float32)
+        base = len(self.payloads)
+        for idx, chunk in enumerate(chunks):
+            d = chunk_as_dict(chunk)
+            self.payloads.append({"chunk_id": d.get("chunk_id", f"chunk_{idx}"), "doc_id": d.get("doc_id", ""),
+                                  "source": d.get("source", ""), "chunk_type": d.get("chunk_type", ""),
+                                  "text": d.get("text", ""), "metadata": d.get("metadata", {})})
+        new = torch.from_numpy(emb).to(torch.bfloat16)
+        if self.rows is not None and base:
+            new = torch.cat([self.rows.cpu(), new])       # point id == position; re-upserts append
+        self.set_rows(new)
+        self._persist()
+        print(f"Successfully indexed {len(chunks)} chunks")
+        print(f"Collection points count: {self.rows.shape[0]}")
+
+    # -- filters: equality on top-level payload keys, applied BEFORE top-k (Qdrant semantics) ------
+    def _row_mask(self, filters: Dict | None):
+        if not filters:
+            return None
+        key = tuple(sorted((k, repr(v)) for k, v in filters.items()))
+        m = self._mask_cache.get(key)
+        if m is None:
+            ok = np.fromiter((all(p.get(k) == v for k, v in filters.items()) for p in self.payloads),
+                             dtype=np.uint8, count=len(self.payloads))
+            m = torch.from_numpy(ok).to(self.device)
+            self._mask_cache[key] = m
+        return m
+
+    # -- batched device API (additive) ---------------------------------------------------------
+    def topk_vectors(self, q_f32: torch.Tensor, kprime: int, row_mask=None, kernel=_lib.DENSE_AUTO):
+        """fp32 device queries [Q, D] -> (scores fp32 [Q,k'], ids int64 [Q,k'], flags int32 [Q])."""
+        return _lib.dense_topk(q_f32, self.rows, self.inv_norm, kprime, row_mask=row_mask, kernel=kernel,
+                               ws=self._ws)
+
+    # -- vector_indexer.py:165-230 ---------------------------------------------------------------
+    def search(self, query: str, top_k: int = 10, filters: Dict = None, score_threshold: float = None) -> List[Dict]:
+        if self.rows is None or self.rows.shape[0] == 0:
+            return []
+        q = np.asarray(self.embedder.encode(query), dtype=np.float32)[:1]
+        qd = torch.from_numpy(np.ascontiguousarray(q)).to(self.device)
+        kprime = max(1, min(top_k, self.rows.shape[0]))
+        scores, ids, _ = self.topk_vectors(qd, kprime, self._row_mask(filters))
+        scores, ids = scores[0].cpu().numpy(), ids[0].cpu().numpy()
+        results = []
+        for idx, s in zip(ids, scores):
+            if idx < 0:
+                break
+            s = float(s)
+            if score_threshold is not None and s < score_threshold:
+                break
+            p = self.payloads[idx]
+            results.append({"chunk_id": p["chunk_id"], "doc_id": p["doc_id"], "source": p["source"],
+                            "chunk_type": p["chunk_type"], "text": p["text"], "metadata": p["metadata"],
+                            "score": s})
+        return results
+
+    def rows_of_texts(self, texts: List[str]) -> List[int]:
+        """Row of each text (-1 if it is not a stored chunk text); used by the simple reranker."""
+        if self._text_rows is None:
+            self._text_rows = {}
+            for i, p in enumerate(self.payloads):
+                self._text_rows.setdefault(p["text"], i)
+        return [self._text_rows.get(t, -1) for t in texts]
+
+    # -- vector_indexer.py:232-250 ---------------------------------------------------------------
+    def get_stats(self) -> Dict:
+        if not self._exists:
+            return {"error": f"Collection {self.collection_name} not found"}
+        return {"collection_name": self.collection_name,
+                "points_count": 0 if self.rows is None else int(self.rows.shape[0]),
+                "embedding_dim": self.embedder.embedding_dim, "model_name": self.embedder.model_name,
+                "storage_path": str(self.storage_path) if self.storage_path else "in-memory"}
+
+    def delete_collection(self, _quiet: bool = False):
+        self.rows, self.inv_norm, self.payloads = None, None, []
+        self._exists = False
+        self._mask_cache.clear()
+        self._text_rows = None
+        if self.storage_path is not None:
+            d = self._dir()
+            for f in ("rows.pt", "payload.pkl"):
+                if (d / f).exists():
+                    (d / f).unlink()
+        if not _quiet:
+            print(f"Deleted collection: {self.collection_name}")

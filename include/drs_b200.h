@@ -1,0 +1,177 @@
+/*
+ * drs_b200.h -- C ABI of the B200-native hybrid-retrieval hot path.
+ *
+ * Drop-in boundary for Luyu-H/Domain-RAG-System's retrieval path.  The reference has
+ * no FFI of its own (pure Python); these entry points are what a binding for that path
+ * binds, one per arithmetic stage the reference delegates to NumPy / rank_bm25 /
+ * qdrant-client.  Reference citations are relative to the reference repository root.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every pointer named d_* is DEVICE memory owned by the caller; the library never
+ *     frees or retains it and allocates no persistent device memory.  Scratch space is
+ *     the caller-provided workspace (size from drs_*_workspace_bytes).
+ *   - All work is enqueued on the caller's stream (cudaStream_t passed as void*); no
+ *     hidden synchronisation, graph-capturable.
+ *   - Return value: 0 on success, negative DRS_ERR_* otherwise; drs_last_error() gives
+ *     the thread-local message.  There is no CPU fallback anywhere.
+ *   - Candidate lists are [Q, k] row-major, sorted by (score desc, row desc) -- the
+ *     determinised form of the reference's `np.argsort(scores)[::-1]` (larger row first
+ *     among exactly equal scores) -- and padded with id -1.
+ */
+#ifndef DRS_B200_H_
+#define DRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRS_OK 0
+#define DRS_ERR_ARG (-1)         /* null pointer, negative size, misaligned pointer */
+#define DRS_ERR_UNSUPPORTED (-2) /* shape outside the compiled limits */
+#define DRS_ERR_WORKSPACE (-3)   /* workspace too small */
+#define DRS_ERR_CUDA (-4)        /* a CUDA call failed; message has the cudaError string */
+
+#define DRS_MAX_KPRIME 128  /* largest per-retriever list length (k' = 2*top_k) */
+#define DRS_MAX_DIM 1024    /* largest embedding dimension; must be a multiple of 8 */
+#define DRS_MAX_POOL 1024   /* largest rerank pool */
+
+/* kernel family selector for drs_dense_topk */
+#define DRS_DENSE_AUTO 0
+#define DRS_DENSE_SIMT 1 /* fp32 CUDA-core streaming kernel (HBM-bound; small Q, any D%8==0) */
+#define DRS_DENSE_UMMA 2 /* tcgen05 bf16 GEMM + fused top-k epilogue (D%64==0, D<=768)    */
+
+int drs_version(void);
+const char* drs_last_error(void);
+
+/* Number of SMs / device properties the library sees on the current device (diagnostic). */
+int drs_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------
+ * Index build helper: inv_norm[r] = 1/||row r||_2 (0 for an all-zero row).
+ * Replaces the upsert-time normalisation qdrant-client's local mode performs for
+ * Distance.COSINE (called from src/indexing/vector_indexer.py:149-154).
+ * ------------------------------------------------------------------------------- */
+int drs_row_inv_norms(const void* d_corpus_bf16, int64_t n_rows, int dim, float* d_inv_norm,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Exact cosine top-k' of Q queries against all N rows.
+ * Replaces QdrantClient.query_points in local mode as called by VectorIndexer.search
+ * (src/indexing/vector_indexer.py:202-209): normalise query, scores = M @ q,
+ * argsort descending, first `limit` hits.
+ *
+ *   d_queries_f32  [Q, dim] fp32 (what MedicalEmbedder.encode returns, embedder.py:50-73)
+ *   d_corpus_bf16  [N, dim] bf16 row-major, 16-byte aligned
+ *   d_inv_norm     [N] from drs_row_inv_norms
+ *   d_row_mask     optional [N] uint8, 0 = row excluded BEFORE top-k (payload filter,
+ *                  vector_indexer.py:185-196); NULL = no filter
+ *   d_out_scores   [Q, kprime] fp32: cosine, exact dot in fp64 rounded once to fp32
+ *   d_out_ids      [Q, kprime] int64 row ids, -1 padded
+ *   d_out_flags    optional [Q] int32: 0 = the result is PROVEN exact w.r.t. the fp64
+ *                  scores; 1 = not proven by the candidate-margin bound (UMMA path only;
+ *                  such queries are re-run through the fp32 kernel when `escalate` != 0)
+ * ------------------------------------------------------------------------------- */
+size_t drs_dense_workspace_bytes(int n_queries, int64_t n_rows, int dim, int kprime, int kernel);
+int drs_dense_topk(const float* d_queries_f32, int n_queries, const void* d_corpus_bf16,
+                   const float* d_inv_norm, const uint8_t* d_row_mask, int64_t n_rows, int dim,
+                   int kprime, int kernel, int escalate, float* d_out_scores, int64_t* d_out_ids,
+                   int32_t* d_out_flags, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * BM25 index on the device: term-major CSR inverted index, document-partitioned into
+ * tiles of `tile_docs` consecutive documents.
+ * Replaces rank_bm25.BM25Okapi (built at src/indexing/bm25_indexer.py:102-106).
+ * ------------------------------------------------------------------------------- */
+typedef struct drs_bm25_index {
+  int64_t n_docs;               /* N                                                     */
+  int32_t n_terms;              /* V                                                     */
+  int32_t tile_docs;            /* documents per tile, power of two, 256..8192          */
+  int32_t n_tiles;              /* ceil(N / tile_docs)                                   */
+  int32_t reserved;
+  const int64_t* d_term_offsets;/* [V+1] postings range of each term                     */
+  const uint32_t* d_post_doc;   /* [nnz] document id, ascending inside a term            */
+  const float* d_post_impact;   /* [nnz] fp32(idf*tf*(k1+1)/(tf+kd[doc]))                */
+  const uint16_t* d_post_tf;    /* [nnz] term frequency (saturated at 65535)             */
+  const uint32_t* d_tile_ptr;   /* [V*(n_tiles+1)] first posting of term t with doc >=
+                                   j*tile_docs, relative to d_term_offsets[t]            */
+  const double* d_idf;          /* [V] idf incl. the epsilon floor (bm25 `idf` dict)     */
+  const double* d_doc_kd;       /* [N] k1*(1-b+b*doc_len/avgdl), fp64, reference op order */
+  double k1_plus_1;             /* k1 + 1                                                */
+} drs_bm25_index;
+
+/* ---------------------------------------------------------------------------------
+ * BM25 top-k' of Q tokenised queries.
+ * Replaces BM25Okapi.get_scores + np.argsort(scores)[::-1][:k'] as called by
+ * BM25Indexer.search (src/indexing/bm25_indexer.py:127-128).
+ *
+ *   d_q_terms    flattened term ids of every query token OCCURRENCE, in order;
+ *                -1 = out-of-vocabulary token (contributes nothing)
+ *   d_q_offsets  [Q+1]
+ *   d_out_scores [Q, kprime] fp64, bit-identical to rank_bm25's fp64 arithmetic
+ *   d_out_ids    [Q, kprime] int64 document ids, -1 padded; zero-score documents ARE
+ *                returned when fewer than k' documents match (reference behaviour)
+ * ------------------------------------------------------------------------------- */
+size_t drs_bm25_workspace_bytes(int n_queries, const drs_bm25_index* index, int kprime);
+int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
+                  int n_queries, int kprime, double* d_out_scores, int64_t* d_out_ids,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Score fusion + final top-K.
+ * Replaces HybridIndexer._reciprocal_rank_fusion (src/indexing/hybrid_indexer.py:112-156)
+ * and HybridIndexer._weighted_fusion (:158-218), arithmetic in fp64 in the reference's
+ * operation order; stable order (ties keep insertion order, vector list first).
+ *
+ *   mode            0 = RRF (uses rrf_k, default 60), 1 = weighted (uses w_vector, w_bm25)
+ *   d_v_* / d_b_*   the two candidate lists [Q, kv] / [Q, kb]; id -1 = absent.  Vector scores
+ *                   are fp32 (v_scores_f64 = 0, what drs_dense_topk emits; widened exactly) or
+ *                   fp64 (v_scores_f64 = 1, caller-built lists); BM25 scores are fp64
+ *   d_fusion_key    optional [n_rows] int64: fusion identity of a row (the reference fuses
+ *                   on chunk_id STRINGS; rows sharing a chunk_id share a key).  NULL = row id
+ *   d_out_ids       [Q, K] representative row of each fused entry (-1 padded)
+ *   d_out_scores    [Q, K] fp64 fused score
+ *   d_out_norm      optional [Q, K] fp64: the `normalized_score` the weighted mode leaks
+ *                   into the representative dict (hybrid_indexer.py:184), NaN if not set
+ * ------------------------------------------------------------------------------- */
+int drs_fuse_topk(int mode, int n_queries, int kv, int kb, const void* d_v_scores, int v_scores_f64,
+                  const int64_t* d_v_ids, const double* d_b_scores, const int64_t* d_b_ids,
+                  const int64_t* d_fusion_key, double rrf_k, double w_vector, double w_bm25, int top_k,
+                  int64_t* d_out_ids, double* d_out_scores, double* d_out_norm, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * "simple" cosine rerank of a pool of rows.
+ * Replaces SimpleSimilarityReranker.score_pairs/_cosine + the stable sort of
+ * BaseReranker.rerank (src/reranker/rerank.py:53-68, :29-43).  Bit-identical to the
+ * reference under NumPy >= 2: three sequential fp32 sums, fp64 sqrt, fp32 divide.
+ *
+ *   d_rq_f32       [Q, dim] fp32 embedding of the RAW query (scripts/query.py:160)
+ *   d_pool_ids     [Q, top_n] rows in fused order, -1 padded
+ *   d_out_scores   [Q, top_k] fp32 rerank_score;  d_out_ids [Q, top_k] rows;
+ *   d_out_pos      optional [Q, top_k] int32 position of each output in the pool
+ * ------------------------------------------------------------------------------- */
+int drs_rerank_cosine(const void* d_corpus_bf16, int dim, const float* d_rq_f32, const int64_t* d_pool_ids,
+                      int n_queries, int top_n, int top_k, float* d_out_scores, int64_t* d_out_ids,
+                      int32_t* d_out_pos, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * Merge of P candidate lists per query into one (the step after the NCCL all-gather of
+ * per-GPU top-k' lists; ids must already be GLOBAL rows).  Input [P, Q, k], output [Q, k_out],
+ * order (score desc, id desc).  No reference counterpart (the reference is single-process);
+ * equals argsort over the concatenation.
+ * ------------------------------------------------------------------------------- */
+int drs_merge_candidates_f32(const float* d_scores, const int64_t* d_ids, int n_parts, int n_queries,
+                             int k, int k_out, float* d_out_scores, int64_t* d_out_ids, void* stream);
+int drs_merge_candidates_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries,
+                             int k, int k_out, double* d_out_scores, int64_t* d_out_ids, void* stream);
+
+/* Last dense call's kernel timing hooks (diagnostic): which kernel family AUTO picked. */
+int drs_dense_last_kernel(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRS_B200_H_ */

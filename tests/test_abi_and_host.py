@@ -1,0 +1,100 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares,
+the host-side index builder matches the oracle, the tokenizer matches the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from domain_rag_system_b200 import _lib, synth
+from domain_rag_system_b200.indexing.bm25_index import Bm25DeviceIndex, choose_tile_docs
+from helpers import load_golden
+from oracle import bm25 as obm25
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "drs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _header_functions()
+    assert len(names) >= 12
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/drs_b200.h but not exported"
+    assert set(_lib.EXPORTS) == set(names)
+    assert _lib.load().drs_version() >= 100
+
+
+def test_product_has_no_cpu_path():
+    """Host tensors are refused; nothing in the package imports the oracle."""
+    with pytest.raises(ValueError):
+        _lib.row_inv_norms(torch.zeros(4, 8, dtype=torch.bfloat16))
+    pkg = os.path.join(ROOT, "domain_rag_system_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+
+
+def test_tokenizer_matches_reference_golden():
+    from domain_rag_system_b200.indexing.bm25_indexer import BM25Indexer
+    bi = BM25Indexer.__new__(BM25Indexer)          # tokenizer only; no device needed
+    from domain_rag_system_b200.indexing.bm25_indexer import _NoAbbreviations
+    bi.normalizer = _NoAbbreviations()
+    for text, toks in load_golden("tokenizer_golden.json"):
+        assert bi.tokenize(text) == toks
+
+    class Abbr:   # a 1-character abbreviation key keeps that token alive (bm25_indexer.py:64-76)
+        abbreviations = {"K": "potassium"}
+    bi.normalizer = Abbr()
+    assert bi.tokenize("serum K level") == ["serum", "k", "level"]
+
+
+@pytest.mark.parametrize("n,vocab", [(1, 4), (37, 11), (600, 400), (5000, 900)])
+def test_host_index_build_matches_oracle(n, vocab):
+    offs, toks = synth.zipf_docs(n, vocab=vocab, seed=5 + n, len_min=1, len_max=40)
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, k1=1.5, b=0.75, device="cpu", tile_docs=256)
+    orc = obm25.Bm25Csr(offs, toks, vocab)
+    assert ix.avgdl == orc.avgdl and ix.average_idf == orc.average_idf
+    assert np.array_equal(ix.t["idf"].numpy(), orc.idf)
+    assert np.array_equal(ix.t["term_offsets"].numpy(), orc.term_offsets)
+    assert np.array_equal(ix.t["post_doc"].numpy().astype(np.int64), orc.post_doc)
+    assert np.array_equal(ix.t["post_tf"].numpy().astype(np.int64), orc.post_tf)
+    kd = 1.5 * (1 - 0.75 + 0.75 * orc.doc_len / orc.avgdl)
+    assert np.array_equal(ix.t["doc_kd"].numpy(), kd)
+    # tile offsets: first posting of term t with doc >= j*tile
+    tp = ix.t["tile_ptr"].numpy()
+    for t in np.random.default_rng(0).integers(0, vocab, size=min(vocab, 25)):
+        docs = orc.post_doc[orc.term_offsets[t]:orc.term_offsets[t + 1]]
+        want = np.searchsorted(docs, np.arange(ix.n_tiles + 1) * ix.tile_docs, side="left")
+        assert np.array_equal(tp[t], want)
+    # fp32 impacts are the rounded fp64 contributions
+    t_of = np.repeat(np.arange(vocab), np.diff(orc.term_offsets))
+    imp = orc.idf[t_of] * (orc.post_tf * 2.5 / (orc.post_tf + kd[orc.post_doc]))
+    assert np.allclose(ix.t["post_impact"].numpy(), imp.astype(np.float32), rtol=1e-6, atol=0)
+
+
+def test_string_corpus_build_assigns_ids_in_first_appearance_order():
+    docs = [["bb", "aa", "bb"], ["cc", "aa"], []]
+    ix = Bm25DeviceIndex.from_token_lists(docs, device="cpu", tile_docs=256)
+    assert ix.vocab == {"bb": 0, "aa": 1, "cc": 2}
+    ref = obm25.BM25OkapiRestated(docs)
+    assert ix.avgdl == ref.avgdl and ix.average_idf == ref.average_idf
+    for w, i in ix.vocab.items():
+        assert ix.t["idf"][i].item() == ref.idf[w]
+    qt, qo = ix.encode_queries([["aa", "zz", "aa"], []])
+    assert qt.tolist() == [1, -1, 1] and qo.tolist() == [0, 3, 3]
+
+
+def test_tile_size_choice():
+    assert choose_tile_docs(600) == 256
+    assert choose_tile_docs(1_000_000) in (1024, 2048)
+    assert choose_tile_docs(10_000_000) == 8192

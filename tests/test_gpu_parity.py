@@ -1,0 +1,381 @@
+"""GPU parity tests: every stage is called through the C ABI (ctypes) and compared with the
+CPU oracle on identical seeded inputs, plus the committed golden fixtures produced by the
+reference's own classes.  Bar (north star): ids exact outside documented score ties, fused
+RRF scores exact, BM25 scores exact, cosine scores within 1e-3 relative (observed ~1e-7)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from domain_rag_system_b200 import _lib, synth
+from domain_rag_system_b200.indexing import (BM25Indexer, Bm25DeviceIndex, HybridIndexer, TableEmbedder,
+                                             VectorIndexer)
+from domain_rag_system_b200.reranker import build_reranker
+from helpers import assert_topk_matches, dicts_to_lists, golden_module, load_golden
+from oracle import bm25 as obm25
+from oracle import dense as odense
+from oracle import fusion as ofusion
+from oracle import rerank as orerank
+from oracle.pipeline import HybridOracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+COS_RTOL = 1e-3   # north-star tolerance for cosine scores
+
+
+def _dense_case(n, q, dim=768, seed=1, dup_frac=0.0):
+    emb = synth.unit_embeddings(n, dim=dim, seed=seed, dup_frac=dup_frac)
+    qv = synth.query_embeddings(q, corpus=emb, dim=dim, seed=seed + 100)
+    return emb, qv
+
+
+def _check_dense(emb_bf16, qv, kprime, kernel, mask=None, escalate=True):
+    rows = emb_bf16.to(DEV)
+    inv = _lib.row_inv_norms(rows)
+    md = None if mask is None else torch.from_numpy(mask.astype(np.uint8)).to(DEV)
+    sc, ids, flags = _lib.dense_topk(qv.to(DEV).contiguous(), rows, inv, kprime, row_mask=md, kernel=kernel,
+                                     escalate=escalate)
+    torch.cuda.synchronize()
+    sc, ids, flags = sc.cpu().numpy(), ids.cpu().numpy(), flags.cpu().numpy()
+    normed = odense.normalize_rows(emb_bf16.float().numpy())
+    ref = odense.cosine_scores_batch(normed, qv.numpy().astype(np.float64))
+    if mask is not None:
+        ref[:, mask == 0] = -np.inf
+    ties = 0
+    n_valid = int(emb_bf16.shape[0] if mask is None else mask.sum())
+    for i in range(qv.shape[0]):
+        k_eff = min(kprime, n_valid)
+        ties += assert_topk_matches(ids[i], sc[i], ref[i], k_eff, COS_RTOL, what=f"dense q{i}")
+        assert (ids[i][k_eff:] == -1).all()
+    return ties, flags
+
+
+# ----------------------------------------------------------------------------------------------
+# dense: fp32 streaming kernel
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kprime", [1, 10, 60, 100, 128])
+def test_dense_simt_golden_corpus(kprime):
+    m = golden_module()
+    emb, _, _, qv, _ = m.hybrid_inputs()
+    emb_bf16 = torch.from_numpy(emb).to(torch.bfloat16)
+    _check_dense(emb_bf16, torch.from_numpy(qv), kprime, _lib.DENSE_SIMT)
+
+
+@pytest.mark.parametrize("n,q,dim", [(1, 1, 768), (7, 2, 768), (1000, 5, 768), (20000, 9, 768), (20000, 4, 384),
+                                     (3000, 3, 64), (3000, 2, 1024), (4097, 1, 200)])
+def test_dense_simt_shapes(n, q, dim):
+    emb, qv = _dense_case(n, q, dim=dim, seed=n + q, dup_frac=0.01 if n > 100 else 0.0)
+    _check_dense(emb, qv, 10, _lib.DENSE_SIMT)
+
+
+def test_dense_simt_filter_mask_zero_rows_zero_query():
+    emb, qv = _dense_case(5000, 4, seed=9)
+    emb[17] = 0          # all-zero row: cosine 0 (qdrant keeps zero vectors as they are)
+    qv[3] = 0            # all-zero query: every score 0 => pure tie order (larger row first)
+    mask = (np.random.default_rng(1).random(5000) < 0.3).astype(np.uint8)
+    _check_dense(emb, qv, 20, _lib.DENSE_SIMT, mask=mask)
+    _check_dense(emb, qv, 20, _lib.DENSE_SIMT)
+    # fewer rows pass the filter than k'
+    mask[:] = 0
+    mask[[5, 99, 4000]] = 1
+    _check_dense(emb, qv, 20, _lib.DENSE_SIMT, mask=mask)
+
+
+# ----------------------------------------------------------------------------------------------
+# dense: tcgen05 kernel (bf16 GEMM + fused top-k), incl. the exactness flags
+# ----------------------------------------------------------------------------------------------
+def _umma_available():
+    ws = _lib.load().drs_dense_workspace_bytes(64, 100000, 768, 10, _lib.DENSE_UMMA)
+    rows = torch.zeros(128, 768, dtype=torch.bfloat16, device=DEV)
+    try:
+        _lib.dense_topk(torch.zeros(16, 768, device=DEV), rows, torch.ones(128, device=DEV), 4, kernel=_lib.DENSE_UMMA)
+        return True
+    except NotImplementedError:
+        return False
+
+
+@pytest.mark.parametrize("n,q,kprime", [(64, 1, 4), (1000, 16, 10), (4099, 130, 10), (50000, 300, 10),
+                                        (50000, 128, 60), (200000, 1000, 10), (30000, 257, 100)])
+def test_dense_umma_matches_oracle(n, q, kprime):
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(n, q, seed=n % 97 + q, dup_frac=0.001)
+    ties, flags = _check_dense(emb, qv, kprime, _lib.DENSE_UMMA)
+    assert set(np.unique(flags).tolist()) <= {0, 2, 3}
+    assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
+
+
+def test_dense_umma_without_escalation_flags_are_conservative():
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(100000, 256, seed=5)
+    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA, escalate=False)
+    assert set(np.unique(flags).tolist()) <= {0, 1}
+    assert (flags == 0).mean() > 0.5   # the bound proves most queries outright
+
+
+def test_dense_umma_mask_and_auto_dispatch():
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(20000, 64, seed=11)
+    mask = (np.random.default_rng(3).random(20000) < 0.5).astype(np.uint8)
+    _check_dense(emb, qv, 10, _lib.DENSE_AUTO, mask=mask)
+    assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
+    _check_dense(emb, qv[:2].contiguous(), 10, _lib.DENSE_AUTO)
+    assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_SIMT
+
+
+# ----------------------------------------------------------------------------------------------
+# BM25
+# ----------------------------------------------------------------------------------------------
+def _check_bm25(offs, toks, vocab, queries, kprime, k1=1.5, b=0.75, tile_docs=None):
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, k1=k1, b=b, device=DEV, tile_docs=tile_docs)
+    orc = obm25.Bm25Csr(offs, toks, vocab, k1=k1, b=b)
+    qt, qo = ix.encode_queries(queries)
+    sc, ids = _lib.bm25_topk(ix.struct(), qt.to(DEV), qo.to(DEV), len(queries), kprime)
+    torch.cuda.synchronize()
+    sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+    n = len(offs) - 1
+    for i, q in enumerate(queries):
+        full = orc.get_scores(q)
+        order = obm25.stable_desc_order(full)[:kprime]
+        k_eff = min(kprime, n)
+        assert np.array_equal(ids[i][:k_eff], order[:k_eff]), f"bm25 q{i}: ids differ"
+        assert np.array_equal(sc[i][:k_eff], full[order[:k_eff]]), f"bm25 q{i}: scores not bit-identical"
+        assert (ids[i][k_eff:] == -1).all()
+
+
+@pytest.mark.parametrize("kprime", [1, 10, 60, 100, 128])
+def test_bm25_golden_corpus(kprime):
+    m = golden_module()
+    _, offs, toks, _, qt = m.hybrid_inputs()
+    _check_bm25(offs, toks, m.HYB["vocab"], qt, kprime)
+
+
+@pytest.mark.parametrize("n,vocab,tile", [(1, 3, None), (300, 40, 256), (20000, 5000, 1024), (70000, 20000, None),
+                                          (9000, 50, 512)])
+def test_bm25_shapes(n, vocab, tile):
+    offs, toks = synth.zipf_docs(n, vocab=vocab, seed=n, len_min=1, len_max=60)
+    qs = synth.zipf_queries(40, offs, toks, vocab=vocab, seed=n + 1)
+    qs += [np.array([], dtype=np.int32), np.array([-1, -1], dtype=np.int32),             # empty / all-OOV
+           np.array([vocab - 1] * 5, dtype=np.int32), np.array([0, 0, 1, 0], dtype=np.int32)]  # rare / repeated head terms
+    _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile)
+    _check_bm25(offs, toks, vocab, qs[:6], 20, k1=1.2, b=0.3, tile_docs=tile)
+
+
+def test_bm25_negative_idf_floor_branch():
+    # tiny vocabulary: the head terms occur in more than half the documents => idf < 0 => eps floor
+    offs, toks = synth.zipf_docs(4000, vocab=12, seed=3, len_min=3, len_max=9)
+    orc = obm25.Bm25Csr(offs, toks, 12)
+    assert (orc.idf == orc.epsilon * orc.average_idf).any()
+    qs = synth.zipf_queries(30, offs, toks, vocab=12, seed=8)
+    _check_bm25(offs, toks, 12, qs, 16)
+
+
+# ----------------------------------------------------------------------------------------------
+# fusion
+# ----------------------------------------------------------------------------------------------
+def test_fusion_dict_api_matches_reference_golden(tmp_path):
+    g = load_golden("fusion_golden.json")
+    hyb = HybridIndexer(None, None, storage_path=str(tmp_path))
+    for entry in g["cases"]:
+        c = entry["case"]
+        rrf = hyb._reciprocal_rank_fusion(copy.deepcopy(c["v"]), copy.deepcopy(c["b"]), top_k=c["top_k"])
+        assert [[r["chunk_id"], r["score"], r["text"]] for r in rrf] == entry["rrf"]
+        assert all(r["fusion_method"] == "rrf" for r in rrf)
+        wf = hyb._weighted_fusion(copy.deepcopy(c["v"]), copy.deepcopy(c["b"]), vector_weight=c["wv"],
+                                  bm25_weight=c["wb"], top_k=c["top_k"])
+        assert [[r["chunk_id"], r["score"], r["text"], r.get("normalized_score")] for r in wf] == entry["weighted"]
+    # known-answer values stored in the reference's results/*.json
+    v = [{"chunk_id": c, "score": 0.5} for c in "abcd"]
+    b = [{"chunk_id": c, "score": 1.0} for c in "xbya"]
+    got = {r["chunk_id"]: r["score"] for r in hyb._reciprocal_rank_fusion(v, b, top_k=10)}
+    assert got["x"] == g["known_answer"]["1/61"] and got["a"] == g["known_answer"]["1/61+1/64"]
+
+
+@pytest.mark.parametrize("mode", ["rrf", "weighted"])
+def test_fusion_batch_matches_oracle(mode):
+    rng = np.random.default_rng(12)
+    nq, kv, kb, n_rows, top_k = 64, 20, 20, 300, 10
+    keys = np.arange(n_rows)
+    keys[rng.integers(0, n_rows, 60)] = rng.integers(0, n_rows, 60)   # rows sharing a chunk_id
+    first = {}
+    keys = np.array([first.setdefault(int(k), i) for i, k in enumerate(keys)])
+    v_ids = np.stack([rng.choice(n_rows, kv, replace=False) for _ in range(nq)])
+    b_ids = np.stack([rng.choice(n_rows, kb, replace=False) for _ in range(nq)])
+    v_sc = -np.sort(-rng.random((nq, kv)).astype(np.float32), axis=1)
+    b_sc = -np.sort(-(rng.random((nq, kb)) * 15), axis=1)
+    b_sc[:, kb // 2:] = 0.0
+    v_ids[3, 10:] = -1          # short lists
+    b_ids[5, :] = -1            # BM25 side empty
+    v_sc[7, :] = 0.25           # max == min => raw scores
+    t = lambda a, dt: torch.from_numpy(a).to(DEV).to(dt)  # noqa: E731
+    ids, sc, _ = _lib.fuse_topk(mode, t(v_sc, torch.float32), t(v_ids, torch.int64), t(b_sc, torch.float64),
+                                t(b_ids, torch.int64), top_k, fusion_key=t(keys, torch.int64), w_vector=0.7,
+                                w_bm25=0.3)
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    names = [f"c{k}" for k in keys]
+    for i in range(nq):
+        v = ofusion.as_dicts(v_ids[i][v_ids[i] >= 0], v_sc[i][v_ids[i] >= 0].astype(np.float64), names)
+        b = ofusion.as_dicts(b_ids[i][b_ids[i] >= 0], b_sc[i][b_ids[i] >= 0], names)
+        ref = ofusion.rrf_fuse(v, b, top_k) if mode == "rrf" else ofusion.weighted_fuse(v, b, 0.7, 0.3, top_k)
+        want_ids = [r["row"] for r in ref] + [-1] * (top_k - len(ref))
+        assert ids[i].tolist() == want_ids, f"fusion q{i}"
+        assert sc[i][: len(ref)].tolist() == [r["score"] for r in ref]    # fp64, bit-exact
+
+
+# ----------------------------------------------------------------------------------------------
+# rerank + merge
+# ----------------------------------------------------------------------------------------------
+def test_rerank_cosine_bit_exact_with_reference_golden():
+    g = load_golden("rerank_golden.json")
+    for p in g["cosine"]:
+        a = np.array(p["a"], dtype=np.float32)
+        b = torch.tensor([p["b"]], dtype=torch.float32)
+        if not torch.equal(b.to(torch.bfloat16).float(), b):
+            continue                      # only bf16-representable rows can live in the corpus
+        sc, ids, pos = _lib.rerank_cosine(b.to(torch.bfloat16).to(DEV), torch.from_numpy(a[None]).to(DEV),
+                                          torch.zeros(1, 1, dtype=torch.int64, device=DEV), 1)
+        assert float(sc[0, 0]) == p["cos"]
+
+
+def test_rerank_order_and_scores_match_oracle():
+    emb, qv = _dense_case(4000, 16, seed=21, dup_frac=0.05)
+    rows = emb.to(DEV)
+    rng = np.random.default_rng(2)
+    pool = np.stack([rng.choice(4000, 50, replace=False) for _ in range(16)])
+    pool[2, 30:] = -1
+    raw = emb.float().numpy()
+    sc, ids, pos = _lib.rerank_cosine(rows, qv.to(DEV), torch.from_numpy(pool).to(DEV), 10)
+    sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+    for i in range(16):
+        valid = pool[i][pool[i] >= 0]
+        s = np.array([orerank.cosine_f32_seq(qv[i].numpy(), raw[r]) for r in valid], dtype=np.float32)
+        order = np.argsort(-s.astype(np.float64), kind="stable")[:10]
+        assert ids[i].tolist() == valid[order].tolist()
+        assert np.array_equal(sc[i], s[order])        # bit-exact
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_merge_candidates_equals_global_sort(dtype):
+    rng = np.random.default_rng(4)
+    p, q, k, k_out = 8, 33, 20, 20
+    sc = rng.random((p, q, k)).astype(np.float32 if dtype == torch.float32 else np.float64)
+    sc[:, :, 5:8] = 0.5                                 # ties across parts
+    ids = rng.permutation(p * q * k).reshape(p, q, k).astype(np.int64)
+    ids[3, :, 15:] = -1
+    out_s, out_i = _lib.merge_candidates(torch.from_numpy(sc).to(DEV), torch.from_numpy(ids).to(DEV), k_out)
+    out_s, out_i = out_s.cpu().numpy(), out_i.cpu().numpy()
+    for j in range(q):
+        s, i = sc[:, j].reshape(-1), ids[:, j].reshape(-1)
+        keep = i >= 0
+        s, i = s[keep], i[keep]
+        order = np.lexsort((-i, -s.astype(np.float64)))[:k_out]
+        assert out_i[j].tolist() == i[order].tolist()
+        assert np.array_equal(out_s[j], s[order])
+
+
+# ----------------------------------------------------------------------------------------------
+# the drop-in classes end to end, against what the REFERENCE's classes returned
+# ----------------------------------------------------------------------------------------------
+def test_dropin_pipeline_matches_reference_golden(tmp_path):
+    from test_oracle_golden import same_up_to_ties
+    g = load_golden("hybrid_golden.json")
+    m = golden_module()
+    emb, offs, toks, qv, qt = m.hybrid_inputs()
+    p = g["params"]
+    texts = synth.docs_as_text(offs, toks)
+    chunks = synth.make_chunks(texts)
+    for r in g["dup_rows"]:
+        chunks[r]["chunk_id"] = chunks[r - 1]["chunk_id"]
+    te = TableEmbedder(dim=768)
+    te.add(texts, emb)
+    qtexts = [" ".join(synth.term_string(t) for t in q) for q in qt]
+    te.add(qtexts, qv)
+    vi = VectorIndexer(collection_name="g", embedder=te, use_in_memory=True)
+    bi = BM25Indexer()
+    hi = HybridIndexer(vi, bi, storage_path=str(tmp_path))
+    hi.index_chunks(chunks)
+    stats = hi.get_stats()
+    assert stats["bm25"] == g["stats"]["bm25"]
+    assert {k: stats["vector"][k] for k in ("points_count", "embedding_dim")} == \
+           {k: g["stats"]["vector"][k] for k in ("points_count", "embedding_dim")}
+    keys = [c["chunk_id"] for c in chunks]
+    orc = HybridOracle(emb, obm25.Bm25Csr(offs, toks, p["vocab"]), chunk_ids=keys)
+    exact = 0
+    for c in g["cases"]:
+        qtext = qtexts[c["q"]]
+        v = vi.search(qtext, top_k=c["top_k"] * 2)
+        b = bi.search(qtext, top_k=c["top_k"] * 2)
+        # BM25 list: scores bit-identical to the reference, ids up to exact ties
+        assert same_up_to_ties(dicts_to_lists(b), c["bm25"])
+        # dense list: ids up to ties, cosine within tolerance
+        gv = c["vector"]
+        assert len(v) == len(gv)
+        assert np.allclose([r["score"] for r in v], [x[2] for x in gv], rtol=COS_RTOL, atol=1e-9)
+        fused = hi.search(qtext, top_k=c["top_k"], fusion_method=c["method"], vector_weight=c["wv"],
+                          bm25_weight=c["wb"])
+        assert all(set(r) >= {"chunk_id", "doc_id", "source", "chunk_type", "text", "metadata", "score",
+                              "fusion_method"} for r in fused)
+        # against the oracle (same deterministic tie rule): ids exact
+        oref = orc.search(qv[c["q"]], qt[c["q"]], top_k=c["top_k"], vector_weight=c["wv"], bm25_weight=c["wb"],
+                          fusion_method=c["method"])
+        assert [r["metadata"]["row"] for r in fused] == [r["row"] for r in oref]
+        if c["method"] == "rrf":
+            assert [r["score"] for r in fused] == [r["score"] for r in oref]            # RRF: exact fp64
+        else:
+            assert np.allclose([r["score"] for r in fused], [r["score"] for r in oref], rtol=COS_RTOL)
+        # against the reference's own output whenever no tie reordered its candidate lists
+        if [x[1] for x in gv] == [r["metadata"]["row"] for r in v] and dicts_to_lists(b) == c["bm25"]:
+            exact += 1
+            assert [r["metadata"]["row"] for r in fused] == [x[1] for x in c["fused"]]
+            if c["method"] == "rrf":
+                assert [r["score"] for r in fused] == [x[2] for x in c["fused"]]
+        if c["top_n"]:
+            rr = build_reranker("simple", top_n=c["top_n"], embedder=te)
+            out = rr.rerank(qtext, fused, top_k=c["final_k"])
+            oout = orc.rerank(qv[c["q"]], oref, top_n=c["top_n"], top_k=c["final_k"])
+            assert [r["metadata"]["row"] for r in out] == [r["row"] for r in oout]
+            assert [r["rerank_score"] for r in out] == [r["rerank_score"] for r in oout]   # bit-exact
+            assert all(r["fusion_method"].endswith("+rerank") for r in out)
+    assert exact >= len(g["cases"]) // 3
+
+
+def test_dropin_error_behaviour(tmp_path):
+    bi = BM25Indexer()
+    with pytest.raises(ValueError, match="Index not built"):
+        bi.search("aspirin")
+    with pytest.raises(FileNotFoundError):
+        bi.load(str(tmp_path / "missing.pkl"))
+    assert bi.get_stats() == {"error": "Index not built"}
+    hi = HybridIndexer(None, None, storage_path=str(tmp_path))
+    assert hi.search("anything") == []
+
+
+def test_search_batch_equals_per_query_search(tmp_path):
+    m = golden_module()
+    emb, offs, toks, qv, qt = m.hybrid_inputs()
+    texts = synth.docs_as_text(offs, toks)
+    chunks = synth.make_chunks(texts)
+    te = TableEmbedder(dim=768)
+    te.add(texts, emb)
+    qtexts = [" ".join(synth.term_string(t) for t in q) for q in qt]
+    te.add(qtexts, qv)
+    vi = VectorIndexer(collection_name="b", embedder=te, use_in_memory=True)
+    bi = BM25Indexer()
+    hi = HybridIndexer(vi, bi, storage_path=str(tmp_path))
+    hi.index_chunks(chunks)
+    q_terms, q_offs = bi.bm25.encode_queries([bi.tokenize(t) for t in qtexts])
+    for method in ("rrf", "weighted"):
+        out = hi.search_batch(torch.from_numpy(qv).to(DEV), q_terms.to(DEV), q_offs.to(DEV), top_k=30,
+                              fusion_method=method, rerank_top_n=30, final_k=5)
+        ids = out["ids"].cpu().numpy()
+        sc = out["scores"].cpu().numpy()
+        rr = build_reranker("simple", top_n=30, embedder=te)
+        for i, t in enumerate(qtexts):
+            one = hi.search(t, top_k=30, fusion_method=method)
+            assert [r["metadata"]["row"] for r in one] == ids[i][: len(one)].tolist()
+            assert [r["score"] for r in one] == sc[i][: len(one)].tolist()
+            rer = rr.rerank(t, one, top_k=5)
+            assert [r["metadata"]["row"] for r in rer] == out["rerank_ids"][i].cpu().tolist()
