@@ -47,7 +47,7 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   const size_t kk = cand_len(kprime);
   const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
   w.simt_parts = dense_simt_grid();
-  w.umma_parts = (which == DRS_DENSE_UMMA) ? dense_umma_parts(n_queries) : 0;
+  w.umma_parts = (which == DRS_DENSE_UMMA) ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0;
   w.umma_qstride = ((n_queries + 127) / 128) * 128;
   const size_t simt_keys = size_t(w.simt_parts) * n_queries * kk;
   const size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk;

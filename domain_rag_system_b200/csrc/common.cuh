@@ -117,7 +117,7 @@ int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, con
                       int q_stride, const int32_t* d_active, cudaStream_t st);
 // dense_umma.cu
 bool dense_umma_supported(int n_queries, int64_t n_rows, int dim, int kk);
-int dense_umma_parts(int n_queries);
+int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk);
 int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                       const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
                       int q_stride, cudaStream_t st);

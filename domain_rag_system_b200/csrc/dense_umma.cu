@@ -1,10 +1,449 @@
-// placeholder until the tcgen05 kernel lands
+// Dense cosine candidate selection on the 5th-gen tensor cores (sm_100a): a persistent,
+// warp-specialised bf16 GEMM  scores[q, row] = queries[q, :] . corpus[row, :]  whose epilogue
+// never writes the scores -- it keeps a per-query running top-kk instead.
+//
+//   A operand  = 128 queries x D, converted fp32 -> bf16 and parked in TENSOR MEMORY for the
+//                whole work item (D/2 <= 384 of the 512 TMEM columns; tcgen05.st, once per item).
+//                Shared memory is therefore free to be a deep ring for the streamed operand.
+//   B operand  = corpus rows, K-major, TMA-loaded (cp.async.bulk.tensor, 128B swizzle) as
+//                64-row x 128-element stages (16 KB) into an mbarrier ring.
+//   D          = 128 x 64 fp32 accumulator tile in the remaining 128 TMEM columns, double
+//                buffered: the epilogue of tile t overlaps the MMAs of tile t+1.
+//   epilogue   = 4 warps; after tcgen05.ld thread L holds query L's 64 scores for the tile, scales
+//                them by inv_norm[row] and compares against its private threshold (the kk-th best so
+//                far); the rare survivors replace the minimum of a private list in shared memory.
+//
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
+// warps 4..7 = A loader + epilogue.  Work item = (block of 128 queries, slab of corpus tiles);
+// items are dealt round-robin so CTAs that run concurrently share corpus tiles through L2.
+// Output: one partial list of kk keys per (slab, query); merged and exactly re-scored downstream.
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
+
 namespace drs {
-bool dense_umma_supported(int, int64_t, int, int) { return false; }
-int dense_umma_parts(int) { return 0; }
-int launch_dense_umma(const float*, int, const void*, const float*, const uint8_t*, int64_t, int, int, uint64_t*, int,
-                      cudaStream_t) {
-  return fail(DRS_ERR_UNSUPPORTED, "tensor-core kernel not built");
+namespace umma {
+
+constexpr int BLOCK_M = 128;                      // queries per item == TMEM lanes
+constexpr int TILE_N = 64;                        // corpus rows per accumulator tile
+constexpr int STAGE_K = 128;                      // K elements per smem stage (two 64-wide TMA boxes)
+constexpr int BOX_K = 64;                         // 64 bf16 = 128 bytes = one swizzle row
+constexpr int BOX_BYTES = TILE_N * BOX_K * 2;     // 8192
+constexpr int STAGE_BYTES = 2 * BOX_BYTES;        // 16384
+constexpr int MAX_D = 768;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_COL0 = MAX_D / 2;               // accumulators live above the A operand
+constexpr int THREADS = 256;
+constexpr int MIN_STAGES = 4;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+// instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TILE_N >> 3) << 17) |
+                           (uint32_t(BLOCK_M >> 4) << 24);
+
+struct Params {
+  const float* queries;
+  const float* inv_norm;
+  const uint8_t* mask;
+  uint64_t* parts;
+  int64_t n_rows;
+  int n_queries, nqb, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
+  uint32_t debug;
+};
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("drs dense_umma: barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand: 8-row x 128-byte atoms, 1024 bytes apart (SBO); descriptor version 1.
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+      "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// replace the minimum of thread L's list by `key`; return the new minimum and its slot
+struct MinSlot {
+  uint64_t key;
+  int pos;
+};
+__device__ __noinline__ MinSlot list_replace_min(uint64_t* lst /* + L */, int kk, int pos, uint64_t key) {
+  lst[pos * BLOCK_M] = key;
+  uint64_t mk = ~0ull;
+  int mp = 0;
+  for (int c = 0; c < kk; ++c) {
+    const uint64_t v = lst[c * BLOCK_M];
+    if (v < mk) {
+      mk = v;
+      mp = c;
+    }
+  }
+  return MinSlot{mk, mp};
+}
+
+__global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
+  extern __shared__ uint8_t smem_dyn[];
+  // carve: [ring | lists | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);
+  uint64_t* bars = lists + size_t(p.kk) * BLOCK_M;
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.n_stages;
+  uint64_t* tfull = bars + 2 * p.n_stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* a_ready = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.nqb * p.n_slabs;
+  const int kst = p.dim / STAGE_K;  // smem stages per accumulator tile
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tfull + 0, 1);
+    mbar_init(tfull + 1, 1);
+    mbar_init(tempty + 0, 4);
+    mbar_init(tempty + 1, 4);
+    mbar_init(a_ready, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(uint32_t(TMEM_COLS))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  auto slab_tiles = [&](int slab, int& t0, int& t1) {
+    t0 = int((int64_t(slab) * p.n_tiles) / p.n_slabs);
+    t1 = int((int64_t(slab + 1) * p.n_tiles) / p.n_slabs);
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t st = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int t0, t1;
+        slab_tiles(item / p.nqb, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          for (int ks = 0; ks < kst; ++ks, ++st) {
+            const uint32_t s = st % p.n_stages, ph = (st / p.n_stages) & 1;
+            mbar_wait(empty + s, ph ^ 1, 1);
+            mbar_arrive_expect_tx(full + s, STAGE_BYTES);
+            uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
+            tma_load_2d(&tmap, full + s, dst, ks * STAGE_K, t * TILE_N);
+            tma_load_2d(&tmap, full + s, dst + BOX_BYTES, ks * STAGE_K + BOX_K, t * TILE_N);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t st = 0, it = 0, item_idx = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_idx) {
+        int t0, t1;
+        slab_tiles(item / p.nqb, t0, t1);
+        mbar_wait(a_ready, item_idx & 1, 2);
+        tc_fence_after();
+        for (int t = t0; t < t1; ++t, ++it) {
+          const uint32_t as = it & 1, aph = (it >> 1) & 1;
+          mbar_wait(tempty + as, aph ^ 1, 3);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ACC_COL0 + as * TILE_N;
+          for (int ks = 0; ks < kst; ++ks, ++st) {
+            const uint32_t s = st % p.n_stages, ph = (st / p.n_stages) & 1;
+            mbar_wait(full + s, ph, 4);
+            tc_fence_after();
+            const uint32_t sbase = smem_u32(ring + size_t(s) * STAGE_BYTES);
+#pragma unroll
+            for (int k16 = 0; k16 < STAGE_K / 16; ++k16) {
+              const uint32_t a_tmem = tmem_base + uint32_t(ks * STAGE_K + k16 * 16) / 2;
+              const uint64_t b_desc = make_b_desc(sbase + (k16 >> 2) * BOX_BYTES + (k16 & 3) * 32);
+              umma_ts(d_tmem, a_tmem, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty + s);  // the stage is free once these MMAs have read it
+          }
+          tc_commit(tfull + as);   // accumulator tile complete
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== A loader + epilogue
+    const int ew = warp - 4;                 // == warp % 4: the TMEM sub-partition this warp may touch
+    const int L = ew * 32 + lane;            // TMEM lane == query within the block
+    const uint32_t lane_addr = uint32_t(ew * 32) << 16;
+    uint64_t* mylist = lists + L;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int qb = item % p.nqb, slab = item / p.nqb;
+      int t0, t1;
+      slab_tiles(slab, t0, t1);
+      // ---- queries -> bf16 -> TMEM (A operand), 64 elements (32 columns) at a time
+      const int q = qb * BLOCK_M + L;
+      const float* qrow = p.queries + size_t(q < p.n_queries ? q : 0) * p.dim;
+      for (int c0 = 0; c0 < p.dim / 2; c0 += 32) {
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < p.n_queries) f = __ldg(reinterpret_cast<const float4*>(qrow + (c0 + j) * 2));
+          __nv_bfloat162 lo = (p.debug & 1) ? __floats2bfloat162_rn(f.y, f.x) : __floats2bfloat162_rn(f.x, f.y);
+          __nv_bfloat162 hi = (p.debug & 1) ? __floats2bfloat162_rn(f.w, f.z) : __floats2bfloat162_rn(f.z, f.w);
+          v[j] = *reinterpret_cast<uint32_t*>(&lo);
+          v[j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        tmem_st32(tmem_base + lane_addr + c0, v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+      // ---- private top-kk list
+      for (int c = 0; c < p.kk; ++c) mylist[c * BLOCK_M] = 0;
+      float tau = -INFINITY;
+      uint64_t tau_key = 0;
+      int min_pos = 0;
+      // inverse norms of the tile's 64 rows: lane l holds rows 2l, 2l+1; broadcast by shuffle
+      auto load_norms = [&](int t, float& n0, float& n1) {
+        const int64_t r = int64_t(t) * TILE_N + 2 * lane;
+        n0 = (t < t1 && r < p.n_rows) ? __ldg(p.inv_norm + r) : 0.f;
+        n1 = (t < t1 && r + 1 < p.n_rows) ? __ldg(p.inv_norm + r + 1) : 0.f;
+      };
+      float nn0, nn1;
+      load_norms(t0, nn0, nn1);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const float n0 = nn0, n1 = nn1;
+        load_norms(t + 1, nn0, nn1);  // prefetch for the next tile
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(tfull + as, aph, 5);
+        tc_fence_after();
+        uint32_t acc0[32], acc1[32];
+        const uint32_t taddr = tmem_base + lane_addr + ACC_COL0 + as * TILE_N;
+        tmem_ld32(taddr, acc0);
+        tmem_ld32(taddr + 32, acc1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + as);  // accumulator stage may be overwritten
+        const int64_t row0 = int64_t(t) * TILE_N;
+        const bool full_tile = (row0 + TILE_N <= p.n_rows);
+#pragma unroll
+        for (int j = 0; j < TILE_N; ++j) {
+          const float nrm = __shfl_sync(0xffffffffu, (j & 1) ? n1 : n0, j >> 1);
+          const float s = __uint_as_float(j < 32 ? acc0[j] : acc1[j - 32]) * nrm;
+          if (s >= tau) {
+            const int64_t row = row0 + j;
+            if ((full_tile || row < p.n_rows) && (p.mask == nullptr || p.mask[row] != 0)) {
+              const uint64_t key = make_key(s, uint32_t(row));
+              if (key > tau_key) {
+                const MinSlot m = list_replace_min(mylist, p.kk, min_pos, key);
+                tau_key = m.key;
+                min_pos = m.pos;
+                tau = m.key ? key_score(m.key) : -INFINITY;
+              }
+            }
+          }
+        }
+      }
+      // ---- hand the list over
+      uint64_t* dst = p.parts + (size_t(slab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
+      for (int c = 0; c < p.kk; ++c) dst[c] = mylist[c * BLOCK_M];
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
+
+struct Plan {
+  int nqb, n_tiles, n_slabs, n_stages, grid;
+  size_t smem;
+};
+
+static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
+  if (dim % STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
+  if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
+  const size_t fixed = 1024 /*align*/ + size_t(kk) * BLOCK_M * 8 + 1024 /*barriers*/;
+  if (fixed + size_t(MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
+  int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
+  if (ns > 12) ns = 12;
+  pl.n_stages = ns;
+  pl.smem = fixed + size_t(ns) * STAGE_BYTES;
+  pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
+  pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
+  const int g = sm_count();
+  int s = g / gcd(g, pl.nqb);
+  if (s > pl.n_tiles) s = pl.n_tiles;
+  pl.n_slabs = s < 1 ? 1 : s;
+  const int items = pl.nqb * pl.n_slabs;
+  pl.grid = items < g ? items : g;
+  return true;
+}
+
+}  // namespace umma
+
+bool dense_umma_supported(int n_queries, int64_t n_rows, int dim, int kk) {
+  umma::Plan pl;
+  return umma::make_plan(n_queries, n_rows, dim, kk, pl) && umma::encode_tiled() != nullptr;
+}
+
+int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk) {
+  umma::Plan pl;
+  return umma::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs : 0;
+}
+
+int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, int q_stride,
+                      cudaStream_t st) {
+  using namespace umma;
+  Plan pl;
+  DRS_REQUIRE(make_plan(n_queries, n_rows, dim, kk, pl), DRS_ERR_UNSUPPORTED,
+              "dense(tcgen05): needs dim % 128 == 0, dim <= 768 and k' small enough for shared memory");
+  EncodeTiledFn enc = encode_tiled();
+  DRS_REQUIRE(enc != nullptr, DRS_ERR_UNSUPPORTED, "dense(tcgen05): cuTensorMapEncodeTiled unavailable");
+  DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0, DRS_ERR_ARG, "dense: queries not 16-byte aligned");
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(n_rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(dim) * 2};
+  const cuuint32_t box[2] = {BOX_K, TILE_N};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_corpus), gdim, gstride, box, estride,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DRS_REQUIRE(r == CUDA_SUCCESS, DRS_ERR_CUDA, "dense(tcgen05): cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+  Params p;
+  p.queries = d_q;
+  p.inv_norm = d_inv_norm;
+  p.mask = d_mask;
+  p.parts = d_parts;
+  p.n_rows = n_rows;
+  p.n_queries = n_queries;
+  p.nqb = pl.nqb;
+  p.dim = dim;
+  p.kk = kk;
+  p.q_stride = q_stride;
+  p.n_slabs = pl.n_slabs;
+  p.n_tiles = pl.n_tiles;
+  p.n_stages = pl.n_stages;
+  const char* dbg = getenv("DRS_UMMA_DEBUG");
+  p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
+  DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+  dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}
+
 }  // namespace drs
