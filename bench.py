@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the hybrid-retrieval hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic queries: dense cosine top-2K
+(tcgen05 GEMM + fused top-k), BM25 top-2K (CSR postings kernel), RRF fusion, top-K -- for
+`--queries` queries against `--chunks` chunks (defaults: configs[1] of BASELINE.json, 1 000
+queries x 1 M chunks x 768-d, top_k 5).  With --gpus N the SAME corpus is row-sharded over the
+N GPUs (strong scaling; one process per GPU, torchrun), each rank does its local top-2K and the
+ranks all-gather the small candidate lists.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+EMB_DIM = 768
+RRF_K = 60
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--top-k", type=int, default=5)
+    ap.add_argument("--fusion", default="rrf", choices=["rrf", "weighted"])
+    ap.add_argument("--vocab", type=int, default=50_000)
+    ap.add_argument("--cpu-sample", type=int, default=8, help="queries timed through the CPU oracle (ours arm)")
+    ap.add_argument("--ref-queries-per-step", type=int, default=4, help="--impl reference: queries per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-kernel", default="auto", choices=["auto", "simt", "umma"])
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"tflops": float(p["bf16_tflops_sustained"]), "tflops_burst": float(p["bf16_tflops"]),
+                "hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    except Exception:
+        return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:  # timed region shorter than the sampling period: use whatever was seen
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0]))
+                    smax = float(f[1])
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------
+def make_queries(args, offs, toks):
+    from domain_rag_system_b200 import synth
+    qv = synth.query_embeddings(args.queries, seed=4321, near_frac=0.0)
+    qt = synth.zipf_queries(args.queries, offs, toks, vocab=args.vocab, seed=777)
+    return qv, qt
+
+
+def cpu_oracle_build(emb_f32, offs, toks, vocab):
+    from oracle import bm25 as obm25
+    from oracle import dense as odense
+    normed = odense.normalize_rows(emb_f32)
+    bm = obm25.Bm25Csr(offs, toks, vocab)
+    return normed, bm
+
+
+def cpu_oracle_query(normed, bm, qvec, qterms, top_k, fusion):
+    """One query through the CPU restatement of HybridIndexer.search, the way the reference
+    runs it: one query at a time, matvec over the whole matrix, argsort, BM25 get_scores,
+    argsort, fusion in Python.  The dense product uses the matrix dtype (fp32 BLAS), the faster
+    of the two plausible qdrant-local behaviours, so the baseline is not understated."""
+    from oracle import bm25 as obm25
+    from oracle import dense as odense
+    from oracle import fusion as ofusion
+    q = np.asarray(qvec, dtype=np.float64)
+    qn = np.linalg.norm(q)
+    q32 = (q / (qn if qn else odense.EPS)).astype(np.float32)
+    sc = normed @ q32
+    vr, vs = odense.dense_search(sc, 2 * top_k)
+    br, bs = obm25.bm25_search(bm.get_scores(qterms), 2 * top_k)
+    v, b = ofusion.as_dicts(vr, vs), ofusion.as_dicts(br, bs)
+    fused = ofusion.rrf_fuse(v, b, top_k) if fusion == "rrf" else ofusion.weighted_fuse(v, b, 0.5, 0.5, top_k)
+    return [r["row"] for r in fused], [r["score"] for r in fused]
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference path on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from domain_rag_system_b200 import synth
+    t_build = time.time()
+    emb = synth.unit_embeddings(args.chunks, seed=1234).float().numpy()
+    offs, toks = synth.zipf_docs(args.chunks, vocab=args.vocab, seed=2025)
+    qv, qt = make_queries(args, offs, toks)
+    normed, bm = cpu_oracle_build(emb, offs, toks, args.vocab)
+    del emb
+    t_build = time.time() - t_build
+    qps_step = args.ref_queries_per_step
+    qi = 0
+
+    def step():
+        nonlocal qi
+        for _ in range(qps_step):
+            cpu_oracle_query(normed, bm, qv[qi % args.queries].numpy(), qt[qi % args.queries], args.top_k, args.fusion)
+            qi += 1
+    for _ in range(args.warmup):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    value = args.steps * qps_step / dt
+    cores = host_threads()
+    line = {
+        "impl": "reference", "metric": "hybrid_topk_queries_per_sec", "value": value, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32/fp64 (CPU)",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{qps_step} sequential queries per step over the full {args.chunks}-chunk corpus "
+                                   f"(NumPy fp32 matvec + CSR fp64 BM25 + Python fusion); index build {t_build:.0f}s untimed"},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE configs[1]: {args.chunks} chunks x {EMB_DIM}-d bf16, {args.queries}-query batch, "
+                        f"top_k={args.top_k}, {args.fusion.upper()} fusion, BM25 Zipf(s=1.07) vocab {args.vocab}",
+            "chunks": args.chunks, "queries_per_step": args.queries, "top_k": args.top_k, "kprime": 2 * args.top_k,
+            "fusion": args.fusion, "dim": EMB_DIM, "vocab": args.vocab,
+            "l2": "inputs larger than L2 (bf16 corpus %.2f GB per pass)" % (args.chunks * EMB_DIM * 2 / 1e9),
+            "parallelism": f"row-sharded x{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from domain_rag_system_b200 import _lib, synth
+    from domain_rag_system_b200.dist import ShardedHybridSearcher, shard_bounds
+    from domain_rag_system_b200.indexing.bm25_index import Bm25DeviceIndex
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    kernel = {"auto": _lib.DENSE_AUTO, "simt": _lib.DENSE_SIMT, "umma": _lib.DENSE_UMMA}[args.dense_kernel]
+
+    # ---- index (resident in HBM before anything is timed) -------------------------------------
+    lo, hi = shard_bounds(args.chunks, world, rank)
+    n_local = hi - lo
+    emb = synth.unit_embeddings(n_local, seed=1234 + rank, device=str(dev))
+    inv = _lib.row_inv_norms(emb)
+    offs, toks = synth.zipf_docs(n_local, vocab=args.vocab, seed=2025 + rank)
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, args.vocab, device=dev, build_device=dev,
+                                        group=True if world > 1 else None)
+    searcher = ShardedHybridSearcher(emb, inv, ix, row_offset=lo)
+
+    # ---- queries (identical on every rank) --------------------------------------------------------
+    if rank == 0:
+        qv, qt = make_queries(args, offs, toks)
+        payload = [qv, qt]
+    else:
+        payload = [None, None]
+    if world > 1:
+        dist.broadcast_object_list(payload, src=0)
+    qv, qt = payload
+    q_terms_h, q_offs_h = ix.encode_queries(qt, pinned=True)
+    qv_h = qv.contiguous().pin_memory()
+    qv_d, q_terms_d, q_offs_d = qv_h.to(dev), q_terms_h.to(dev), q_offs_h.to(dev)
+    ids_h = torch.empty(args.queries, args.top_k, dtype=torch.int64).pin_memory()
+    sc_h = torch.empty(args.queries, args.top_k, dtype=torch.float64).pin_memory()
+    h2d = qv_h.numel() * 4 + q_terms_h.numel() * 4 + q_offs_h.numel() * 4
+    d2h = ids_h.numel() * 8 + sc_h.numel() * 8
+
+    def step_resident():
+        return searcher.search_batch(qv_d, q_terms_d, q_offs_d, top_k=args.top_k, fusion_method=args.fusion,
+                                     dense_kernel=kernel)
+
+    def step_e2e():
+        qv_d.copy_(qv_h, non_blocking=True)
+        q_terms_d.copy_(q_terms_h, non_blocking=True)
+        q_offs_d.copy_(q_offs_h, non_blocking=True)
+        ids, sc = step_resident()
+        ids_h.copy_(ids, non_blocking=True)
+        sc_h.copy_(sc, non_blocking=True)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.load().drs_kernel_launches()
+    _lib.profile_enable(True)
+    t0 = time.time()
+    ms_total = timed(step_resident, args.steps)
+    t1 = time.time()
+    prof = _lib.profile_read()
+    _lib.profile_enable(False)
+    launches = int(_lib.load().drs_kernel_launches() - launches0)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    ms_step = ms_total / args.steps
+    value = args.queries / (ms_step / 1e3)
+    e2e_value = args.queries / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel (dense GEMM + fused top-k) ---------------------------------
+    peaks = measured_peaks()
+    d_ms, d_n = prof["dense_select"]
+    flops = 2.0 * args.queries * n_local * EMB_DIM
+    dense_tflops = flops / (d_ms / max(d_n, 1) / 1e3) / 1e12 if d_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("dense_select_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "dense_umma_kernel" if _lib.load().drs_dense_last_kernel() == 2 else "dense_simt_kernel",
+                "bound": "tensor", "achieved": dense_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": dense_tflops / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
+                "frac_of_nominal_2250": dense_tflops / 2250.0, "flops_per_launch": flops,
+                "ms_per_launch": d_ms / max(d_n, 1), "launches": d_n}
+    b_ms, b_n = prof["bm25_select"]
+    sum_df = int(ix.df_of(q_terms_h.numpy()).sum())
+    bm_bytes = 8.0 * sum_df
+    bm_gbs = bm_bytes / (b_ms / max(b_n, 1) / 1e3) / 1e9 if b_ms > 0 else 0.0
+    roofline_bm25 = {"kernel": "bm25_select_kernel", "bound": "hbm", "achieved": bm_gbs, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": bm_gbs / peaks["hbm_gbs"], "bytes_per_launch": bm_bytes,
+                     "sum_df_per_batch": sum_df, "ms_per_launch": b_ms / max(b_n, 1)}
+    breakdown = {k: (v[0] / args.steps) for k, v in prof.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline + recall on a bounded sample (rank 0, single GPU only) ------------------------
+    cpu_baseline, recall = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        ids_gpu, sc_gpu = step_resident()
+        ids_gpu, sc_gpu = ids_gpu.cpu().numpy(), sc_gpu.cpu().numpy()
+        normed, bm = cpu_oracle_build(emb.float().cpu().numpy(), offs, toks, args.vocab)
+        ns = min(args.cpu_sample, args.queries)
+        cpu_oracle_query(normed, bm, qv[0].numpy(), qt[0], args.top_k, args.fusion)   # warm
+        t = time.time()
+        ref = [cpu_oracle_query(normed, bm, qv[i].numpy(), qt[i], args.top_k, args.fusion) for i in range(ns)]
+        dt = time.time() - t
+        hit = sum(len(set(ref[i][0]) & set(ids_gpu[i].tolist())) for i in range(ns))
+        exact = sum(ref[i][0] == ids_gpu[i].tolist() for i in range(ns))
+        recall = {"recall_at_k": hit / float(ns * args.top_k), "queries_identical": exact, "sample": ns}
+        cpu_baseline = {"value": ns / dt, "unit": "queries/s", "cores": host_threads(), "kind": "port",
+                        "sample": f"{ns} sequential queries over the full {args.chunks}-chunk corpus through the CPU "
+                                  "oracle (NumPy fp32 matvec + CSR fp64 BM25 + Python fusion)"}
+
+    line = {
+        "metric": "hybrid_topk_queries_per_sec", "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16 (dense GEMM, fp32 accumulate) + fp64 (BM25/fusion)",
+        "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "roofline": roofline, "roofline_bm25": roofline_bm25,
+        "kernel_ms_per_step": breakdown, "cpu_baseline": cpu_baseline, "parity": recall, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

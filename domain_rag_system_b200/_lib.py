@@ -33,6 +33,9 @@ EXPORTS = {
     "drs_last_error": (C.c_char_p, []),
     "drs_device_sm_count": (C.c_int, []),
     "drs_dense_last_kernel": (C.c_int, []),
+    "drs_kernel_launches": (C.c_ulonglong, []),
+    "drs_profile_enable": (C.c_int, [_i32]),
+    "drs_profile_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "drs_row_inv_norms": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "drs_dense_workspace_bytes": (_sz, [_i32, _i64, _i32, _i32, _i32]),
     "drs_dense_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -88,6 +91,23 @@ def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise ValueError("drs: device tensors required (no CPU path exists)")
+
+
+PROF_KINDS = {"dense_select": 0, "dense_tail": 1, "bm25_select": 2, "bm25_tail": 3, "fuse": 4, "rerank": 5}
+
+
+def profile_enable(on: bool):
+    _check(load().drs_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{kind: (total_ms, launches)} since the last profile_enable(True); synchronises."""
+    out = {}
+    for name, k in PROF_KINDS.items():
+        ms, n = C.c_double(0.0), C.c_int(0)
+        _check(load().drs_profile_read(k, C.byref(ms), C.byref(n)))
+        out[name] = (ms.value, n.value)
+    return out
 
 
 class Workspace:

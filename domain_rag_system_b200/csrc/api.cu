@@ -1,7 +1,9 @@
 // C-ABI plumbing: error string, device query, and the dense top-k orchestration
 // (candidate selection -> k-way merge -> exact re-score -> optional fp32 re-run of unproven queries).
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -9,6 +11,8 @@ namespace drs {
 
 static thread_local std::string g_last_error;
 static thread_local int g_last_dense_kernel = 0;
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches += (unsigned long long)n; }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
@@ -26,6 +30,38 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+// ---- measurement hooks -------------------------------------------------------------------
+struct ProfKind {
+  std::vector<cudaEvent_t> start, stop;
+  size_t used = 0;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static ProfKind g_prof[DRS_PROF_KINDS];
+constexpr size_t PROF_MAX_LAUNCHES = 1 << 14;
+
+void prof_begin(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfKind& k = g_prof[kind];
+  if (k.used >= PROF_MAX_LAUNCHES) return;
+  if (k.used == k.start.size()) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+    k.start.push_back(a);
+    k.stop.push_back(b);
+  }
+  cudaEventRecord(k.start[k.used], st);
+}
+void prof_end(int kind, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfKind& k = g_prof[kind];
+  if (k.used >= k.start.size()) return;
+  cudaEventRecord(k.stop[k.used], st);
+  ++k.used;
 }
 
 static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
@@ -67,6 +103,30 @@ extern "C" const char* drs_last_error(void) { return g_last_error.c_str(); }
 extern "C" int drs_device_sm_count(void) { return sm_count(); }
 extern "C" int drs_dense_last_kernel(void) { return g_last_dense_kernel; }
 
+extern "C" unsigned long long drs_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int drs_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& k : g_prof) k.used = 0;
+  return DRS_OK;
+}
+extern "C" int drs_profile_read(int kind, double* total_ms, int* launches) {
+  DRS_REQUIRE(kind >= 0 && kind < DRS_PROF_KINDS && total_ms && launches, DRS_ERR_ARG, "profile: bad arguments");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfKind& k = g_prof[kind];
+  double ms = 0.0;
+  for (size_t i = 0; i < k.used; ++i) {
+    DRS_CUDA_CHECK(cudaEventSynchronize(k.stop[i]));
+    float t = 0.f;
+    DRS_CUDA_CHECK(cudaEventElapsedTime(&t, k.start[i], k.stop[i]));
+    ms += t;
+  }
+  *total_ms = ms;
+  *launches = int(k.used);
+  return DRS_OK;
+}
+
 extern "C" size_t drs_dense_workspace_bytes(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
   if (n_queries < 0 || n_rows < 0 || kprime <= 0 || kprime > DRS_MAX_KPRIME) return 0;
   return dense_ws(n_queries, n_rows, dim, kprime, kernel).total;
@@ -98,17 +158,25 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   g_last_dense_kernel = which;
   int rc;
   if (which == DRS_DENSE_SIMT) {
-    rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
-                           n_queries, nullptr, st);
+    {
+      ProfScope ps(DRS_PROF_DENSE_SELECT, st);
+      rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                             n_queries, nullptr, st);
+    }
     if (rc != DRS_OK) return rc;
+    ProfScope pt(DRS_PROF_DENSE_TAIL, st);
     rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk, cand, nullptr, st);
     if (rc != DRS_OK) return rc;
     return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 4e-6f,
                                 d_out_scores, d_out_ids, flags, nullptr, 0, 1, 0, st);
   }
-  rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
-                         w.umma_qstride, st);
+  {
+    ProfScope ps(DRS_PROF_DENSE_SELECT, st);
+    rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                           w.umma_qstride, st);
+  }
   if (rc != DRS_OK) return rc;
+  ProfScope pt(DRS_PROF_DENSE_TAIL, st);
   rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, st);
   if (rc != DRS_OK) return rc;
   rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,

@@ -243,13 +243,19 @@ extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_ter
   DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8, st));
   const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
   DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  bm25_select_kernel<<<dim3(gx, gy), BM25_THREADS, smem, st>>>(ix, d_q_terms, d_q_offsets, n_queries, kk, tpc,
-                                                               parts, n_queries, gtau);
+  {
+    ProfScope ps(DRS_PROF_BM25_SELECT, st);
+    bm25_select_kernel<<<dim3(gx, gy), BM25_THREADS, smem, st>>>(ix, d_q_terms, d_q_offsets, n_queries, kk, tpc,
+                                                                 parts, n_queries, gtau);
+    count_launches(1);
+  }
   DRS_CUDA_CHECK(cudaGetLastError());
+  ProfScope pt(DRS_PROF_BM25_TAIL, st);
   int rc = launch_merge_keys(parts, gx, n_queries, n_queries, kk, cand, nullptr, st);
   if (rc != DRS_OK) return rc;
   bm25_rescore_kernel<<<n_queries, 256, 0, st>>>(ix, d_q_terms, d_q_offsets, cand, kk, kprime, d_out_scores,
                                                  d_out_ids);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

@@ -29,6 +29,17 @@ int fail(int code, const std::string& msg);
   } while (0)
 
 int sm_count();
+void count_launches(int n);   // bumps the process-wide kernel-launch counter (drs_kernel_launches)
+
+// measurement hooks (api.cu): no-ops unless drs_profile_enable(1) was called
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+  int kind;
+  cudaStream_t st;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(k, s); }
+  ~ProfScope() { prof_end(kind, st); }
+};
 
 // ---- sortable keys -------------------------------------------------------------------
 // A candidate is (score, row).  Order everywhere: score descending, then row descending

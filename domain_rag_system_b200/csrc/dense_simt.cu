@@ -215,6 +215,7 @@ static int launch_one(const float* d_q, int n_queries, int q0, const void* d_cor
   kern<<<grid, SIMT_THREADS, smem, st>>>(d_q, n_queries, q0, reinterpret_cast<const __nv_bfloat16*>(d_corpus),
                                           d_inv_norm, d_mask, n_rows, dim, rows_per_cta, kk, d_parts, q_stride,
                                           d_active, pass);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

@@ -442,6 +442,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
   DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

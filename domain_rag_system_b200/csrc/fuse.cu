@@ -168,9 +168,11 @@ extern "C" int drs_fuse_topk(int mode, int n_queries, int kv, int kb, const void
                   d_out_scores,
               DRS_ERR_ARG, "fuse: null pointer");
   if (n_queries == 0) return DRS_OK;
+  ProfScope ps(DRS_PROF_FUSE, (cudaStream_t)stream);
   fuse_kernel<<<n_queries, FUSE_THREADS, 0, (cudaStream_t)stream>>>(
       mode, kv, kb, d_v_scores, v_scores_f64, d_v_ids, d_b_scores, d_b_ids, d_fusion_key, rrf_k, w_vector, w_bm25, top_k,
       d_out_ids, d_out_scores, d_out_norm);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

@@ -102,8 +102,10 @@ extern "C" int drs_rerank_cosine(const void* d_corpus_bf16, int dim, const float
   if (n_queries == 0) return DRS_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int threads = ((top_n + 31) / 32) * 32;
+  ProfScope ps(DRS_PROF_RERANK, st);
   rerank_kernel<<<n_queries, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(d_corpus_bf16), dim, d_rq_f32,
                                                d_pool_ids, top_n, top_k, d_out_scores, d_out_ids, d_out_pos);
+  count_launches(1);
   cudaError_t e = cudaGetLastError();
   DRS_CUDA_CHECK(e);
   return DRS_OK;
@@ -118,6 +120,7 @@ extern "C" int drs_row_inv_norms(const void* d_corpus_bf16, int64_t n_rows, int 
   const int blocks = int(std::min<int64_t>((n_rows + 7) / 8, int64_t(sm_count()) * 16));
   row_inv_norm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(d_corpus_bf16),
                                                                n_rows, dim, d_inv_norm);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

@@ -46,6 +46,7 @@ int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_
                       uint64_t* d_out, const int32_t* d_active, cudaStream_t st) {
   DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2, DRS_ERR_UNSUPPORTED, "merge: list length out of range");
   merge_keys_kernel<<<n_queries, 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_out, d_active);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }
@@ -176,6 +177,7 @@ int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, 
                                                    d_inv_norm, dim, d_cand, kk, kprime, approx_err,
                                                    d_out_scores, d_out_ids, d_flags, d_active,
                                                    query_rounded_bf16, flag_unproven, flag_proven);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }
@@ -249,6 +251,7 @@ static int merge_pairs(const ScoreT* d_scores, const int64_t* d_ids, int n_parts
   if (n_queries == 0) return DRS_OK;
   merge_pairs_kernel<ScoreT><<<n_queries, 256, 0, (cudaStream_t)stream>>>(
       d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids);
+  count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }

@@ -46,6 +46,8 @@ class Bm25DeviceIndex:
         self.average_idf = 0.0
         self.vocab: Dict[str, int] | None = None   # term string -> id (None for id-only corpora)
         self.vocab_present = 0                     # number of distinct terms that occur
+        self.row_offset = 0                        # global row of local document 0 (sharded corpora)
+        self.n_docs_global = 0
         self.total_tokens = 0
         self.t: Dict[str, torch.Tensor] = {}       # device tensors
         self._struct = None
@@ -58,8 +60,13 @@ class Bm25DeviceIndex:
     # -----------------------------------------------------------------------------
     @classmethod
     def from_token_ids(cls, doc_offsets, tokens, vocab_size: int, k1=1.5, b=0.75, epsilon=0.25,
-                       device="cuda", tile_docs: int | None = None, build_device=None):
-        """``doc_offsets`` int64 [N+1], ``tokens`` int32 [total] (term ids in [0, vocab_size))."""
+                       device="cuda", tile_docs: int | None = None, build_device=None, group=None):
+        """``doc_offsets`` int64 [N+1], ``tokens`` int32 [total] (term ids in [0, vocab_size)).
+
+        ``group``: a ``torch.distributed`` process group (or ``True`` for the default group) when
+        this rank holds one ROW SHARD of a larger corpus.  BM25's statistics are global (df, N,
+        avgdl, and the order in which idf values are summed), so they are reduced across ranks
+        once, here; postings keep LOCAL document ids and ``row_offset`` maps them to global rows."""
         self = cls()
         build_device = torch.device(build_device or device)
         device = torch.device(device)
@@ -70,7 +77,21 @@ class Bm25DeviceIndex:
         total = int(offs[-1])
         self.n_docs, self.n_terms, self.k1, self.b, self.epsilon = n, int(vocab_size), k1, b, epsilon
         self.total_tokens = total
-        self.avgdl = total / n
+        n_global, total_global, tok_offset = n, total, 0
+        dist = None
+        if group is not None:
+            import torch.distributed as dist
+            grp = None if group is True else group
+            world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+            sizes = torch.zeros(world, 2, dtype=torch.int64, device=build_device)
+            sizes[rank, 0], sizes[rank, 1] = n, total
+            dist.all_reduce(sizes, group=grp)
+            sizes = sizes.cpu()
+            n_global, total_global = int(sizes[:, 0].sum()), int(sizes[:, 1].sum())
+            self.row_offset = int(sizes[:rank, 0].sum())
+            tok_offset = int(sizes[:rank, 1].sum())
+        self.n_docs_global = n_global
+        self.avgdl = total_global / n_global
         doc_len = (offs[1:] - offs[:-1]).to(build_device)
         toks = torch.as_tensor(np.asarray(tokens)).to(build_device, dtype=torch.int64)
         doc_of_tok = torch.repeat_interleave(torch.arange(n, device=build_device, dtype=torch.int64), doc_len)
@@ -89,7 +110,15 @@ class Bm25DeviceIndex:
             first_pos.scatter_reduce_(0, toks, torch.arange(total, device=build_device, dtype=torch.int64),
                                       reduce="amin", include_self=True)
         del toks
-        df_h = df.cpu().numpy()
+        df_stat = df
+        if dist is not None:
+            first_pos = torch.where(first_pos < total, first_pos + tok_offset,
+                                    torch.full_like(first_pos, torch.iinfo(torch.int64).max))
+            dist.all_reduce(first_pos, op=dist.ReduceOp.MIN, group=grp)
+            df_stat = df.clone()
+            dist.all_reduce(df_stat, group=grp)
+        df_h = df_stat.cpu().numpy()
+        n_local, n = n, n_global          # idf uses the GLOBAL corpus size
         order = np.argsort(first_pos.cpu().numpy(), kind="stable")
         idf = np.zeros(self.n_terms, dtype=np.float64)
         idf_sum = 0
@@ -111,6 +140,7 @@ class Bm25DeviceIndex:
         self.average_idf = idf_sum / present
         if neg:
             idf[np.array(neg, dtype=np.int64)] = self.epsilon * self.average_idf
+        n = n_local
         # per-document length normaliser, fp64, reference operation order
         dl_h = doc_len.cpu().numpy()
         kd_h = self.k1 * (1 - self.b + self.b * dl_h / self.avgdl)
@@ -223,7 +253,8 @@ class Bm25DeviceIndex:
         return {"meta": dict(n_docs=self.n_docs, n_terms=self.n_terms, tile_docs=self.tile_docs, n_tiles=self.n_tiles,
                              k1=self.k1, b=self.b, epsilon=self.epsilon, avgdl=self.avgdl,
                              average_idf=self.average_idf, vocab_present=self.vocab_present,
-                             total_tokens=self.total_tokens),
+                             total_tokens=self.total_tokens, row_offset=self.row_offset,
+                             n_docs_global=self.n_docs_global),
                 "vocab": self.vocab, "tensors": {k: v.cpu() for k, v in self.t.items()}}
 
     @classmethod

@@ -168,8 +168,27 @@ int drs_merge_candidates_f32(const float* d_scores, const int64_t* d_ids, int n_
 int drs_merge_candidates_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries,
                              int k, int k_out, double* d_out_scores, int64_t* d_out_ids, void* stream);
 
-/* Last dense call's kernel timing hooks (diagnostic): which kernel family AUTO picked. */
+/* Which kernel family the last drs_dense_topk call on this thread used (DRS_DENSE_SIMT/UMMA). */
 int drs_dense_last_kernel(void);
+
+/* ---------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): when enabled, the library brackets its kernels with CUDA
+ * events on the caller's stream, per kernel family, so the device time of the dominant
+ * kernel can be read without a profiler.  drs_profile_read synchronises on the recorded
+ * events and returns the summed milliseconds and the number of launches since the last
+ * drs_profile_enable(1).
+ * ------------------------------------------------------------------------------- */
+#define DRS_PROF_DENSE_SELECT 0 /* tcgen05 GEMM+top-k kernel or the fp32 streaming kernel */
+#define DRS_PROF_DENSE_TAIL 1   /* merge + exact re-score (+ escalation)                   */
+#define DRS_PROF_BM25_SELECT 2  /* postings scatter/accumulate + tile top-k                */
+#define DRS_PROF_BM25_TAIL 3    /* merge + fp64 re-score                                   */
+#define DRS_PROF_FUSE 4
+#define DRS_PROF_RERANK 5
+#define DRS_PROF_KINDS 6
+/* kernels launched by this library in this process so far */
+unsigned long long drs_kernel_launches(void);
+int drs_profile_enable(int on);
+int drs_profile_read(int kind, double* total_ms, int* launches);
 
 #ifdef __cplusplus
 }
