@@ -74,13 +74,13 @@ static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim,
 }
 
 struct DenseWs {
-  size_t parts_keys, cand_keys, flags_off, total;
+  size_t parts_keys, cand_keys, flags_off, gtau_off, total;
   int simt_parts, umma_parts, umma_qstride;
 };
 
 static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
   DenseWs w{};
-  const size_t kk = cand_len(kprime);
+  const size_t kk = cand_len_umma(kprime);   // the longer of the two candidate lengths sizes every buffer
   const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
   w.simt_parts = dense_simt_grid();
   w.umma_parts = (which == DRS_DENSE_UMMA) ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0;
@@ -90,7 +90,8 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   w.parts_keys = std::max(simt_keys, umma_keys);
   w.cand_keys = size_t(n_queries) * kk;
   w.flags_off = (w.parts_keys + w.cand_keys) * 8;
-  w.total = w.flags_off + size_t(n_queries) * 4 + 256;
+  w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
+  w.total = w.gtau_off + size_t(w.umma_qstride) * 4 + 256;
   return w;
 }
 
@@ -145,7 +146,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   DRS_REQUIRE(n_rows < (int64_t(1) << 32), DRS_ERR_UNSUPPORTED, "dense: more than 2^32-1 rows in one shard");
   DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus_bf16) & 15) == 0, DRS_ERR_ARG, "dense: corpus not 16-byte aligned");
   if (n_queries == 0) return DRS_OK;
-  const int kk = cand_len(kprime);
+  const int kk_s = cand_len(kprime), kk = cand_len_umma(kprime);
   const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, kk);
   DRS_REQUIRE(which > 0, DRS_ERR_UNSUPPORTED, "dense: tensor-core kernel does not support this shape");
   const DenseWs w = dense_ws(n_queries, n_rows, dim, kprime, kernel);
@@ -160,35 +161,36 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   if (which == DRS_DENSE_SIMT) {
     {
       ProfScope ps(DRS_PROF_DENSE_SELECT, st);
-      rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+      rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk_s, parts,
                              n_queries, nullptr, st);
     }
     if (rc != DRS_OK) return rc;
     ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-    rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk, cand, nullptr, st);
+    rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, nullptr, st);
     if (rc != DRS_OK) return rc;
-    return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 4e-6f,
-                                d_out_scores, d_out_ids, flags, nullptr, 0, 1, 0, st);
+    return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk_s, kprime, 4e-6f,
+                                d_out_scores, d_out_ids, flags, nullptr, DRS_QMODE_EXACT, 1, 0, st);
   }
   {
     ProfScope ps(DRS_PROF_DENSE_SELECT, st);
     rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
-                           w.umma_qstride, st);
+                           w.umma_qstride,
+                           reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off), st);
   }
   if (rc != DRS_OK) return rc;
   ProfScope pt(DRS_PROF_DENSE_TAIL, st);
   rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, st);
   if (rc != DRS_OK) return rc;
   rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
-                            d_out_scores, d_out_ids, flags, nullptr, 1, 1, 0, st);
+                            d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st);
   if (rc != DRS_OK || !escalate) return rc;
   // Re-run the (few) queries whose tensor-core result is not proven exact through the fp32 kernel.
   // Everything is predicated on flags[] on the device; with no flagged query the kernels exit at once.
-  rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+  rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk_s, parts,
                          n_queries, flags, st);
   if (rc != DRS_OK) return rc;
-  rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk, cand, flags, st);
+  rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, flags, st);
   if (rc != DRS_OK) return rc;
-  return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 4e-6f,
-                              d_out_scores, d_out_ids, flags, flags, 0, 3, 2, st);
+  return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk_s, kprime, 4e-6f,
+                              d_out_scores, d_out_ids, flags, flags, DRS_QMODE_EXACT, 3, 2, st);
 }

@@ -19,8 +19,10 @@
 namespace drs {
 
 constexpr int BM25_THREADS = 256;
-constexpr int BM25_MBUF = 4096;  // merge buffer (u64 keys): list + candidate append area
+constexpr int BM25_MBUF = 2048;  // merge buffer (u64 keys): list + candidate append area
+constexpr int BM25_TCHUNK = 64;  // query term occurrences whose posting ranges are staged per tile at once
 constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
+constexpr int BM25_MERGE_AT = 512;  // survivors that justify a re-sort (warm list)
 
 __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
@@ -31,6 +33,7 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
   float* sc = reinterpret_cast<float*>(mbuf + BM25_MBUF);                // [tile_docs]
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
+  __shared__ long long s_a[BM25_TCHUNK], s_e[BM25_TCHUNK];  // posting ranges of the staged terms in this tile
 
   const int T = ix.tile_docs;
   const int tid = threadIdx.x;
@@ -72,27 +75,60 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
       for (int i = tid; i < T; i += BM25_THREADS) sc[i] = 0.0f;
       __syncthreads();
       // ---- accumulate: one term occurrence at a time, in query order -------------------
-      for (int ti = t0; ti < t1; ++ti) {
-        const int t = q_terms[ti];
-        if (t < 0 || t >= ix.n_terms) continue;  // OOV: contributes nothing (block-uniform)
-        const int64_t base = ix.d_term_offsets[t];
-        const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
-        const int64_t a = base + tp[0], e = base + tp[1];
-        int64_t p = a + tid;
-        for (; p + 3 * BM25_THREADS < e; p += 4 * BM25_THREADS) {
-          const uint32_t d0 = __ldg(ix.d_post_doc + p), d1 = __ldg(ix.d_post_doc + p + BM25_THREADS);
-          const uint32_t d2 = __ldg(ix.d_post_doc + p + 2 * BM25_THREADS),
-                         d3 = __ldg(ix.d_post_doc + p + 3 * BM25_THREADS);
-          const float i0 = __ldg(ix.d_post_impact + p), i1 = __ldg(ix.d_post_impact + p + BM25_THREADS);
-          const float i2 = __ldg(ix.d_post_impact + p + 2 * BM25_THREADS),
-                      i3 = __ldg(ix.d_post_impact + p + 3 * BM25_THREADS);
-          sc[d0 - doc0] += i0;
-          sc[d1 - doc0] += i1;
-          sc[d2 - doc0] += i2;
-          sc[d3 - doc0] += i3;
+      // The ranges [a, e) of every staged term inside this tile are fetched by separate threads in one
+      // go (term id -> term offset -> tile pointer is a chain of dependent loads; paying it once per
+      // tile instead of once per term keeps the loop below on streaming loads only).
+      for (int c0 = t0; c0 < t1; c0 += BM25_TCHUNK) {
+      const int nstaged = min(BM25_TCHUNK, t1 - c0);
+      if (tid < nstaged) {
+        const int t = q_terms[c0 + tid];
+        long long a = 0, e = 0;
+        if (t >= 0 && t < ix.n_terms) {  // OOV: contributes nothing
+          const long long base = ix.d_term_offsets[t];
+          const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+          a = base + tp[0];
+          e = base + tp[1];
         }
-        for (; p < e; p += BM25_THREADS) sc[__ldg(ix.d_post_doc + p) - doc0] += __ldg(ix.d_post_impact + p);
+        s_a[tid] = a;
+        s_e[tid] = e;
+      }
+      __syncthreads();
+      for (int ti = 0; ti < nstaged; ++ti) {
+        const int64_t a = s_a[ti], e = s_e[ti];
+        if (a >= e) continue;  // block-uniform: nothing written, no barrier needed
+        // head (to 16-byte alignment), vector body (4 postings per thread per load), tail
+        int64_t a4 = (a + 3) & ~int64_t(3);
+        if (a4 > e) a4 = e;
+        if (a + tid < a4) sc[__ldg(ix.d_post_doc + a + tid) - doc0] += __ldg(ix.d_post_impact + a + tid);
+        const int64_t nvec = (e - a4) >> 2;
+        const uint4* dv = reinterpret_cast<const uint4*>(ix.d_post_doc + a4);
+        const float4* iv = reinterpret_cast<const float4*>(ix.d_post_impact + a4);
+        int64_t v = tid;
+        for (; v + BM25_THREADS < nvec; v += 2 * BM25_THREADS) {
+          const uint4 d0 = __ldg(dv + v), d1 = __ldg(dv + v + BM25_THREADS);
+          const float4 i0 = __ldg(iv + v), i1 = __ldg(iv + v + BM25_THREADS);
+          sc[d0.x - doc0] += i0.x;
+          sc[d0.y - doc0] += i0.y;
+          sc[d0.z - doc0] += i0.z;
+          sc[d0.w - doc0] += i0.w;
+          sc[d1.x - doc0] += i1.x;
+          sc[d1.y - doc0] += i1.y;
+          sc[d1.z - doc0] += i1.z;
+          sc[d1.w - doc0] += i1.w;
+        }
+        for (; v < nvec; v += BM25_THREADS) {
+          const uint4 d0 = __ldg(dv + v);
+          const float4 i0 = __ldg(iv + v);
+          sc[d0.x - doc0] += i0.x;
+          sc[d0.y - doc0] += i0.y;
+          sc[d0.z - doc0] += i0.z;
+          sc[d0.w - doc0] += i0.w;
+        }
+        const int64_t ts = a4 + (nvec << 2);
+        if (ts + tid < e) sc[__ldg(ix.d_post_doc + ts + tid) - doc0] += __ldg(ix.d_post_impact + ts + tid);
         __syncthreads();
+      }
+      __syncthreads();  // ranges may be restaged
       }
       // ---- scan the tile, highest document first -----------------------------------------
       for (int seg = 0; seg < T; seg += BM25_SEG) {
@@ -109,11 +145,13 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
           }
         }
         __syncthreads();
-        // merge when the append area could overflow in the next segment, while the list is still
-        // filling (so a threshold exists as early as possible), and at the end of the tile
-        const bool last = (seg + BM25_SEG >= T);
+        // Merge (sort list + survivors, tighten the threshold) when the append area could overflow in
+        // the next segment, when enough survivors piled up that a tighter threshold pays for the
+        // sort, as soon as a cold list can be filled, and at the very end of this CTA's tiles.
+        const bool last = (seg + BM25_SEG >= T) && (j == tile_lo);
         const int cnt = s_cnt;
-        if (cnt > 0 && (last || cnt > cap - BM25_SEG || mbuf[kk - 1] == 0)) merge(q);
+        if (cnt > 0 && (last || cnt > cap - BM25_SEG || cnt >= BM25_MERGE_AT || (mbuf[kk - 1] == 0 && cnt >= kk)))
+          merge(q);
       }
     }
     for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];
@@ -190,16 +228,22 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
   }
 }
 
+// Grid: x = runs of consecutive tiles, y = query groups.  A CTA walks ALL its tiles for one query
+// before moving to the next query, so its threshold is warm after the first tile; with many queries
+// we therefore want FEW x-slices (long runs) and many y-groups, keeping ~8 (slice, query) work units
+// per resident CTA for balance.  With one query every tile gets its own CTA.
 static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& gy, int& tiles_per_cta) {
   const int target = 4 * sm_count();
-  gx = ix->n_tiles < target ? ix->n_tiles : target;
+  const int q = n_queries > 0 ? n_queries : 1;
+  gx = (8 * target + q - 1) / q;
+  if (gx > ix->n_tiles) gx = ix->n_tiles;
   if (gx < 1) gx = 1;
   tiles_per_cta = (ix->n_tiles + gx - 1) / gx;
   if (tiles_per_cta < 1) tiles_per_cta = 1;
   gx = (ix->n_tiles + tiles_per_cta - 1) / tiles_per_cta;
   if (gx < 1) gx = 1;
   gy = (target + gx - 1) / gx;
-  if (gy > n_queries) gy = n_queries;
+  if (gy > q) gy = q;
   if (gy < 1) gy = 1;
   if (gy > 65535) gy = 65535;
 }

@@ -108,9 +108,17 @@ __host__ __device__ __forceinline__ int next_pow2(int v) {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// how the selection stage represented the query (drives the exactness bound in dense_rescore)
+#define DRS_QMODE_EXACT 0      /* fp32 query, fp32 FMA accumulation (streaming kernel)            */
+#define DRS_QMODE_BF16_RAW 1   /* query rounded to bf16, approximate scores NOT scaled by 1/||q|| */
+
 // candidate-list length carried through the approximate stages: k' plus a margin that the
 // exact re-scoring stage consumes (see DESIGN.md "exactness").
 __host__ __device__ __forceinline__ int cand_len(int kprime) { return kprime + 8 + (kprime >> 2); }
+// The tensor-core kernel ranks rows with a bf16-rounded query (score error up to ~2e-3), so it
+// carries a wider margin: the exactness proof needs the gap between the k'-th exact and the
+// kk-th approximate score to exceed that error, which k'+24 makes near-certain.
+__host__ __device__ __forceinline__ int cand_len_umma(int kprime) { return kprime + 24 + (kprime >> 2); }
 
 // ---- launchers implemented in the .cu files ---------------------------------------------
 // select.cu
@@ -119,7 +127,7 @@ int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_
 int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                          int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
-                         const int32_t* d_active, int query_rounded_bf16, int flag_unproven, int flag_proven,
+                         const int32_t* d_active, int query_mode, int flag_unproven, int flag_proven,
                          cudaStream_t st);
 // dense_simt.cu
 int dense_simt_grid();
@@ -129,8 +137,9 @@ int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, con
 // dense_umma.cu
 bool dense_umma_supported(int n_queries, int64_t n_rows, int dim, int kk);
 int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk);
+int dense_umma_query_mode();  // DRS_QMODE_* the tensor-core kernel will use
 int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                       const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
-                      int q_stride, cudaStream_t st);
+                      int q_stride, uint32_t* d_gtau, cudaStream_t st);
 
 }  // namespace drs

@@ -39,7 +39,9 @@ constexpr int ACC_COL0 = MAX_D / 2;               // accumulators live above the
 constexpr int THREADS = 256;
 constexpr int MIN_STAGES = 4;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
-// instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
+// instruction descriptor: D=f32, A=B=bf16, both operands K-major, N=64, M=128.  (A and B must share
+// the format: the hardware rejects fp16 x bf16 inside one kind::f16 MMA as an illegal instruction,
+// so the query cannot be carried at fp16 precision while the corpus is bf16.)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TILE_N >> 3) << 17) |
                            (uint32_t(BLOCK_M >> 4) << 24);
 
@@ -48,6 +50,7 @@ struct Params {
   const float* inv_norm;
   const uint8_t* mask;
   uint64_t* parts;
+  uint32_t* gtau;  // [q_stride] zero-initialised shared thresholds
   int64_t n_rows;
   int n_queries, nqb, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
   uint32_t debug;
@@ -139,24 +142,40 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
-
-// replace the minimum of thread L's list by `key`; return the new minimum and its slot
-struct MinSlot {
-  uint64_t key;
-  int pos;
-};
-__device__ __noinline__ MinSlot list_replace_min(uint64_t* lst /* + L */, int kk, int pos, uint64_t key) {
-  lst[pos * BLOCK_M] = key;
-  uint64_t mk = ~0ull;
-  int mp = 0;
-  for (int c = 0; c < kk; ++c) {
-    const uint64_t v = lst[c * BLOCK_M];
-    if (v < mk) {
-      mk = v;
-      mp = c;
-    }
+// ---- per-thread candidate list ------------------------------------------------------------
+__device__ __forceinline__ uint64_t lds_u64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  return v;
+}
+// Thread-private MIN-HEAP of kk keys in shared memory (slot c of lane L at lst + c*LSTRIDE:
+// column-major over the 128 lanes, conflict-free).  The root is the kk-th best candidate so far
+// (0 while the list is not full: empty slots are zero keys), so replacing it costs O(log kk).
+constexpr uint32_t LSTRIDE = BLOCK_M * 8;
+__device__ __forceinline__ uint64_t heap_replace_root(uint32_t lst, int kk, uint64_t key) {
+  int i = 0;
+  while (true) {
+    const int l = 2 * i + 1;
+    if (l >= kk) break;
+    const int r = l + 1;
+    const uint64_t kl = lds_u64(lst + l * LSTRIDE);
+    const uint64_t kr = (r < kk) ? lds_u64(lst + r * LSTRIDE) : ~0ull;
+    const bool right = kr < kl;
+    const uint64_t kc = right ? kr : kl;
+    if (kc >= key) break;
+    sts_u64(lst + i * LSTRIDE, kc);
+    i = right ? r : l;
   }
-  return MinSlot{mk, mp};
+  sts_u64(lst + i * LSTRIDE, key);
+  return lds_u64(lst);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
@@ -171,6 +190,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
   uint64_t* tempty = tfull + 2;
   uint64_t* a_ready = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  float* norm_strips = reinterpret_cast<float*>(                  // [4 warps][2][TILE_N], 16-byte aligned
+      (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.nqb * p.n_slabs;
@@ -261,7 +282,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
     const int ew = warp - 4;                 // == warp % 4: the TMEM sub-partition this warp may touch
     const int L = ew * 32 + lane;            // TMEM lane == query within the block
     const uint32_t lane_addr = uint32_t(ew * 32) << 16;
-    uint64_t* mylist = lists + L;
+    const uint32_t mylist = smem_u32(lists) + uint32_t(L) * 8;  // shared-space address of this thread's slot 0
+    float* norm_strip = norm_strips + ew * 2 * TILE_N;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int qb = item % p.nqb, slab = item / p.nqb;
@@ -269,17 +291,18 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       slab_tiles(slab, t0, t1);
       // ---- queries -> bf16 -> TMEM (A operand), 64 elements (32 columns) at a time
       const int q = qb * BLOCK_M + L;
-      const float* qrow = p.queries + size_t(q < p.n_queries ? q : 0) * p.dim;
+      const bool live = q < p.n_queries;
+      const float* qrow = p.queries + size_t(live ? q : 0) * p.dim;
       for (int c0 = 0; c0 < p.dim / 2; c0 += 32) {
         uint32_t v[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < p.n_queries) f = __ldg(reinterpret_cast<const float4*>(qrow + (c0 + j) * 2));
-          __nv_bfloat162 lo = (p.debug & 1) ? __floats2bfloat162_rn(f.y, f.x) : __floats2bfloat162_rn(f.x, f.y);
-          __nv_bfloat162 hi = (p.debug & 1) ? __floats2bfloat162_rn(f.w, f.z) : __floats2bfloat162_rn(f.z, f.w);
-          v[j] = *reinterpret_cast<uint32_t*>(&lo);
-          v[j + 1] = *reinterpret_cast<uint32_t*>(&hi);
+          if (live) f = __ldg(reinterpret_cast<const float4*>(qrow + (c0 + j) * 2));
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(f.x, f.y);
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(f.z, f.w);
+          v[j] = *reinterpret_cast<const uint32_t*>(&lo);
+          v[j + 1] = *reinterpret_cast<const uint32_t*>(&hi);
         }
         tmem_st32(tmem_base + lane_addr + c0, v);
       }
@@ -287,12 +310,18 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
-      // ---- private top-kk list
-      for (int c = 0; c < p.kk; ++c) mylist[c * BLOCK_M] = 0;
-      float tau = -INFINITY;
-      uint64_t tau_key = 0;
-      int min_pos = 0;
-      // inverse norms of the tile's 64 rows: lane l holds rows 2l, 2l+1; broadcast by shuffle
+      // ---- private top-kk min-heap; its root is the kk-th best candidate once the list is full
+      for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
+      uint64_t root = 0;
+      float tau_loc = -INFINITY;
+      // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by
+      // every slab working on q (ordered-u32 image, atomicMax).  A row scoring below it cannot be
+      // in the global top-kk, so slabs warm each other's thresholds.  Padding lanes never insert.
+      uint32_t* gt = p.gtau + (live ? q : 0);
+      uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
+      const bool no_insert = (p.debug & 2) != 0;
+      // inverse norms of the tile's 64 rows: lane l fetches rows 2l, 2l+1 (prefetched one tile ahead),
+      // parks them in this warp's shared-memory strip, and every lane reads all 64 by broadcast
       auto load_norms = [&](int t, float& n0, float& n1) {
         const int64_t r = int64_t(t) * TILE_N + 2 * lane;
         n0 = (t < t1 && r < p.n_rows) ? __ldg(p.inv_norm + r) : 0.f;
@@ -301,8 +330,12 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       float nn0, nn1;
       load_norms(t0, nn0, nn1);
       for (int t = t0; t < t1; ++t, ++it) {
-        const float n0 = nn0, n1 = nn1;
+        float* nbuf = norm_strip + (it & 1) * TILE_N;
+        reinterpret_cast<float2*>(nbuf)[lane] = make_float2(nn0, nn1);
+        __syncwarp();
         load_norms(t + 1, nn0, nn1);  // prefetch for the next tile
+        float tau = live ? fmaxf(tau_loc, g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
+        if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);  // lands while this tile is processed
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(tfull + as, aph, 5);
         tc_fence_after();
@@ -311,32 +344,65 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         tmem_ld32(taddr, acc0);
         tmem_ld32(taddr + 32, acc1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + as);  // accumulator stage may be overwritten
-        const int64_t row0 = int64_t(t) * TILE_N;
-        const bool full_tile = (row0 + TILE_N <= p.n_rows);
+        // ---- pass 1, branch-free: which of my 64 scores reach the threshold?
+        uint32_t m0 = 0, m1 = 0;
+        const float4* nb4 = reinterpret_cast<const float4*>(nbuf);
 #pragma unroll
-        for (int j = 0; j < TILE_N; ++j) {
-          const float nrm = __shfl_sync(0xffffffffu, (j & 1) ? n1 : n0, j >> 1);
-          const float s = __uint_as_float(j < 32 ? acc0[j] : acc1[j - 32]) * nrm;
-          if (s >= tau) {
+        for (int g = 0; g < 8; ++g) {
+          const float4 n = nb4[g];
+          m0 |= (__uint_as_float(acc0[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+          m0 |= (__uint_as_float(acc0[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+          m0 |= (__uint_as_float(acc0[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+          m0 |= (__uint_as_float(acc0[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 n = nb4[8 + g];
+          m1 |= (__uint_as_float(acc1[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+          m1 |= (__uint_as_float(acc1[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+          m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+          m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+        }
+        if (no_insert) m0 = m1 = 0;
+        // ---- pass 2, rare and rolled: for every column some lane flagged, all lanes re-read that one
+        // accumulator column from TMEM (the load is warp-collective) and the flagged lanes insert.
+        uint32_t u0 = __reduce_or_sync(0xffffffffu, m0), u1 = __reduce_or_sync(0xffffffffu, m1);
+        const int64_t row0 = int64_t(t) * TILE_N;
+        while (u0 | u1) {
+          int j;
+          if (u0) {
+            j = __ffs(u0) - 1;
+            u0 &= u0 - 1;
+          } else {
+            j = 32 + __ffs(u1) - 1;
+            u1 &= u1 - 1;
+          }
+          const uint32_t v = tmem_ld1(taddr + j);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const bool mine = (((j < 32) ? (m0 >> j) : (m1 >> (j - 32))) & 1u) != 0;
+          if (mine) {
+            const float s = __uint_as_float(v) * nbuf[j];
             const int64_t row = row0 + j;
-            if ((full_tile || row < p.n_rows) && (p.mask == nullptr || p.mask[row] != 0)) {
+            if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
               const uint64_t key = make_key(s, uint32_t(row));
-              if (key > tau_key) {
-                const MinSlot m = list_replace_min(mylist, p.kk, min_pos, key);
-                tau_key = m.key;
-                min_pos = m.pos;
-                tau = m.key ? key_score(m.key) : -INFINITY;
+              if (key > root) {
+                root = heap_replace_root(mylist, p.kk, key);
+                if (root) {
+                  tau_loc = key_score(root);
+                  tau = fmaxf(tau, tau_loc);
+                  atomicMax(gt, ord32(tau_loc));
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty + as);  // accumulator stage may be overwritten
       }
       // ---- hand the list over
       uint64_t* dst = p.parts + (size_t(slab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
-      for (int c = 0; c < p.kk; ++c) dst[c] = mylist[c * BLOCK_M];
+      for (int c = 0; c < p.kk; ++c) dst[c] = lds_u64(mylist + c * LSTRIDE);
     }
   }
 
@@ -376,7 +442,7 @@ struct Plan {
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
   if (dim % STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
   if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
-  const size_t fixed = 1024 /*align*/ + size_t(kk) * BLOCK_M * 8 + 1024 /*barriers*/;
+  const size_t fixed = 1024 /*align*/ + size_t(kk) * BLOCK_M * 8 + 4096 /*barriers, tmem slot, norm strips*/;
   if (fixed + size_t(MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
   if (ns > 12) ns = 12;
@@ -400,6 +466,8 @@ bool dense_umma_supported(int n_queries, int64_t n_rows, int dim, int kk) {
   return umma::make_plan(n_queries, n_rows, dim, kk, pl) && umma::encode_tiled() != nullptr;
 }
 
+int dense_umma_query_mode() { return DRS_QMODE_BF16_RAW; }
+
 int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk) {
   umma::Plan pl;
   return umma::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs : 0;
@@ -407,7 +475,7 @@ int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk) {
 
 int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                       const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, int q_stride,
-                      cudaStream_t st) {
+                      uint32_t* d_gtau, cudaStream_t st) {
   using namespace umma;
   Plan pl;
   DRS_REQUIRE(make_plan(n_queries, n_rows, dim, kk, pl), DRS_ERR_UNSUPPORTED,
@@ -429,6 +497,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.inv_norm = d_inv_norm;
   p.mask = d_mask;
   p.parts = d_parts;
+  p.gtau = d_gtau;
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -440,6 +509,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_stages = pl.n_stages;
   const char* dbg = getenv("DRS_UMMA_DEBUG");
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * sizeof(uint32_t), st));
   DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   count_launches(1);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
     const float* __restrict__ queries, const __nv_bfloat16* __restrict__ corpus,
     const float* __restrict__ inv_norm, int dim, const uint64_t* __restrict__ cand, int kk, int kprime,
     float approx_err, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
-    int32_t* __restrict__ flags, const int32_t* __restrict__ active, int query_rounded_bf16,
+    int32_t* __restrict__ flags, const int32_t* __restrict__ active, int query_mode,
     int flag_value_unproven, int flag_value_proven) {
   __shared__ float sq[DRS_MAX_DIM];
   __shared__ uint64_t ekey[RESCORE_MAXC];
@@ -79,33 +79,38 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
   if (active != nullptr && active[q] == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // query -> smem, ||q||^2 and ||q - bf16(q)||^2 in fp64
-  double part = 0.0, perr = 0.0;
+  // query -> smem; ||q||^2 in fp64; and the L2 norm of the error the selection stage made by
+  // rounding the query (bf16 of the raw query)
+  double part = 0.0;
   for (int i = threadIdx.x; i < dim; i += blockDim.x) {
     float v = queries[size_t(q) * dim + i];
     sq[i] = v;
     part += double(v) * double(v);
-    const double d = double(v) - double(__bfloat162float(__float2bfloat16_rn(v)));
-    perr += d * d;
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    part += __shfl_xor_sync(0xffffffffu, part, o);
-    perr += __shfl_xor_sync(0xffffffffu, perr, o);
-  }
-  if (lane == 0) {
-    red[warp] = part;
-    red2[warp] = perr;
-  }
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[warp] = part;
   if (threadIdx.x == 0) s_nvalid = 0;
   __syncthreads();
-  double qn2 = 0.0, qe2 = 0.0;
-  for (int w = 0; w < 8; ++w) {
-    qn2 += red[w];
-    qe2 += red2[w];
-  }
+  double qn2 = 0.0;
+  for (int w = 0; w < 8; ++w) qn2 += red[w];
   const double inv_q = qn2 > 0.0 ? 1.0 / sqrt(qn2) : 0.0;
-  // Cauchy-Schwarz: |(q - bf16(q)) . c| * inv_norm[c] * inv_q <= ||q - bf16(q)|| * inv_q  (||c||*inv_norm = 1)
-  const float err_bound = approx_err + (query_rounded_bf16 ? float(sqrt(qe2) * inv_q * 1.0001) : 0.0f);
+  double perr = 0.0;
+  if (query_mode != DRS_QMODE_EXACT) {
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+      const float v = sq[i];
+      const double d = (double(v) - double(__bfloat162float(__float2bfloat16_rn(v)))) * inv_q;
+      perr += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) perr += __shfl_xor_sync(0xffffffffu, perr, o);
+  }
+  __syncthreads();
+  if (lane == 0) red2[warp] = perr;
+  __syncthreads();
+  double qe2 = 0.0;
+  for (int w = 0; w < 8; ++w) qe2 += red2[w];
+  // Cauchy-Schwarz: |(q_used - q/||q||) . c| * inv_norm[c] <= ||q_used - q/||q|| ||   (||c||*inv_norm = 1)
+  const float err_bound = approx_err + float(sqrt(qe2) * 1.0001);
+  const double amin_scale = inv_q;  // approximate scores are not scaled by 1/||q||
 
   const int m = next_pow2(kk);
   for (int i = threadIdx.x; i < m; i += blockDim.x) ekey[i] = 0;
@@ -160,7 +165,7 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
     int f = flag_value_proven;
     if (s_nvalid >= kk && kprime <= kk) {  // list was full: rows outside it exist
       const float tau = key_score(ekey[kprime - 1]);
-      const float outside_best = float(double(s_amin) * inv_q) + err_bound;
+      const float outside_best = float(double(s_amin) * amin_scale) + err_bound;
       f = (outside_best < tau) ? 0 : flag_value_unproven;
     }
     flags[q] = f;
@@ -170,13 +175,13 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
 int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                          int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
-                         const int32_t* d_active, int query_rounded_bf16, int flag_unproven, int flag_proven,
+                         const int32_t* d_active, int query_mode, int flag_unproven, int flag_proven,
                          cudaStream_t st) {
   DRS_REQUIRE(kk <= RESCORE_MAXC, DRS_ERR_UNSUPPORTED, "rescore: candidate list too long");
   dense_rescore_kernel<<<n_queries, 256, 0, st>>>(d_q, reinterpret_cast<const __nv_bfloat16*>(d_corpus),
                                                    d_inv_norm, dim, d_cand, kk, kprime, approx_err,
                                                    d_out_scores, d_out_ids, d_flags, d_active,
-                                                   query_rounded_bf16, flag_unproven, flag_proven);
+                                                   query_mode, flag_unproven, flag_proven);
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;

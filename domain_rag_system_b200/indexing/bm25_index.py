@@ -27,9 +27,12 @@ from .. import _lib
 
 
 def choose_tile_docs(n_docs: int, sm_count: int = 148) -> int:
-    t = 256
-    while t < 8192 and n_docs // t > 4 * sm_count:
-        t *= 2
+    """Documents per tile (power of two, 256..8192).  Large tiles amortise the per-(tile, query)
+    costs (zeroing, range lookup, scan) and are the default; small corpora get smaller tiles so a
+    single query still spreads over ~64 CTAs."""
+    t = 8192
+    while t > 256 and n_docs // t < 64:
+        t //= 2
     return t
 
 

@@ -115,6 +115,18 @@ def test_dense_umma_without_escalation_flags_are_conservative():
     assert (flags == 0).mean() > 0.5   # the bound proves most queries outright
 
 
+def test_dense_umma_unnormalised_queries_and_proof_rate():
+    """Cosine is scale-invariant: un-normalised queries work, and with the k'+24 candidate margin the
+    rounding bound proves (nearly) every query exact without the fp32 re-run."""
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(60000, 200, seed=13)
+    qv[5] *= 37.5
+    qv[6] *= 1e-3
+    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA, escalate=False)
+    assert (flags == 0).mean() > 0.97
+
+
 def test_dense_umma_mask_and_auto_dispatch():
     if not _umma_available():
         pytest.skip("tcgen05 kernel not built")
