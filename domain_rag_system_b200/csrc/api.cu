@@ -91,7 +91,7 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   w.cand_keys = size_t(n_queries) * kk;
   w.flags_off = (w.parts_keys + w.cand_keys) * 8;
   w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
-  w.total = w.gtau_off + size_t(w.umma_qstride) * 4 + 256;
+  w.total = w.gtau_off + size_t(w.umma_qstride) * 4 * (1 + size_t(w.umma_parts)) + 256;
   return w;
 }
 

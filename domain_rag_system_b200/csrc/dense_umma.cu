@@ -51,9 +51,11 @@ struct Params {
   const uint8_t* mask;
   uint64_t* parts;
   uint32_t* gtau;  // [q_stride] zero-initialised shared thresholds
+  uint32_t* gslab; // [n_slabs][q_stride] zero-initialised: each slab's m_rank-th best inserted score
   int64_t n_rows;
   int n_queries, nqb, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
   uint32_t debug;
+  int m_rank;      // ceil(kk / n_slabs) if <= 4 and all slabs run concurrently, else 0 (pooling off)
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -97,6 +99,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* b
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// one lane of a fully converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred)::"memory");
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -229,51 +241,64 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      uint32_t st = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        int t0, t1;
-        slab_tiles(item / p.nqb, t0, t1);
-        for (int t = t0; t < t1; ++t) {
-          for (int ks = 0; ks < kst; ++ks, ++st) {
-            const uint32_t s = st % p.n_stages, ph = (st / p.n_stages) & 1;
-            mbar_wait(empty + s, ph ^ 1, 1);
+    uint32_t s = 0, ph = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int t0, t1;
+      slab_tiles(item / p.nqb, t0, t1);
+      for (int t = t0; t < t1; ++t) {
+        for (int ks = 0; ks < kst; ++ks) {
+          mbar_wait(empty + s, ph ^ 1, 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(full + s, STAGE_BYTES);
             uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
             tma_load_2d(&tmap, full + s, dst, ks * STAGE_K, t * TILE_N);
             tma_load_2d(&tmap, full + s, dst + BOX_BYTES, ks * STAGE_K + BOX_K, t * TILE_N);
+          }
+          __syncwarp();
+          if (++s == uint32_t(p.n_stages)) {
+            s = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t st = 0, it = 0, item_idx = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_idx) {
-        int t0, t1;
-        slab_tiles(item / p.nqb, t0, t1);
-        mbar_wait(a_ready, item_idx & 1, 2);
+    // The WHOLE warp walks the loops (so every address below is warp-uniform and lives in uniform
+    // registers); one elected lane issues the tcgen05 instructions.  A tile's 48 MMAs take 32 tensor
+    // cycles each, so the issue path must stay within a handful of instructions per MMA.
+    uint32_t st = 0, it = 0, item_idx = 0;
+    uint32_t s = 0, ph = 0;   // ring slot / phase, stepped without divisions
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_idx) {
+      int t0, t1;
+      slab_tiles(item / p.nqb, t0, t1);
+      mbar_wait(a_ready, item_idx & 1, 2);
+      tc_fence_after();
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(tempty + as, aph ^ 1, 3);
         tc_fence_after();
-        for (int t = t0; t < t1; ++t, ++it) {
-          const uint32_t as = it & 1, aph = (it >> 1) & 1;
-          mbar_wait(tempty + as, aph ^ 1, 3);
+        const uint32_t d_tmem = tmem_base + ACC_COL0 + as * TILE_N;
+        for (int ks = 0; ks < kst; ++ks, ++st) {
+          mbar_wait(full + s, ph, 4);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ACC_COL0 + as * TILE_N;
-          for (int ks = 0; ks < kst; ++ks, ++st) {
-            const uint32_t s = st % p.n_stages, ph = (st / p.n_stages) & 1;
-            mbar_wait(full + s, ph, 4);
-            tc_fence_after();
-            const uint32_t sbase = smem_u32(ring + size_t(s) * STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t desc0 = make_b_desc(smem_u32(ring + size_t(s) * STAGE_BYTES));
+            const uint32_t a0 = tmem_base + uint32_t(ks) * (STAGE_K / 2);
 #pragma unroll
             for (int k16 = 0; k16 < STAGE_K / 16; ++k16) {
-              const uint32_t a_tmem = tmem_base + uint32_t(ks * STAGE_K + k16 * 16) / 2;
-              const uint64_t b_desc = make_b_desc(sbase + (k16 >> 2) * BOX_BYTES + (k16 & 3) * 32);
-              umma_ts(d_tmem, a_tmem, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
+              // +32 bytes per K=16 step inside a 128-byte swizzle row, +8 KB for the second box
+              const uint64_t b_desc = desc0 + uint64_t((k16 >> 2) * (BOX_BYTES >> 4) + (k16 & 3) * 2);
+              umma_ts(d_tmem, a0 + k16 * 8, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
             }
-            tc_commit(empty + s);  // the stage is free once these MMAs have read it
+            tc_commit(empty + s);                      // the stage is free once these MMAs have read it
+            if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
           }
-          tc_commit(tfull + as);   // accumulator tile complete
+          __syncwarp();
+          if (++s == uint32_t(p.n_stages)) {
+            s = 0;
+            ph ^= 1;
+          }
         }
       }
     }
@@ -319,6 +344,15 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       // in the global top-kk, so slabs warm each other's thresholds.  Padding lanes never insert.
       uint32_t* gt = p.gtau + (live ? q : 0);
       uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
+      // Pooled threshold.  All n_slabs slabs of a query block run CONCURRENTLY (one item per CTA), each
+      // publishes the m-th best score it has inserted so far (m = ceil(kk / n_slabs) <= 4) in
+      // gslab[slab][q].  If every slab has m rows scoring >= x, the corpus has >= kk such rows, so
+      // x = min over slabs is a valid lower bound on the global kk-th best -- and a far tighter one than
+      // any single slab's own kk-th best while all the lists are still warming up.
+      volatile uint32_t* gs = p.gslab + size_t(slab) * p.q_stride + (live ? q : 0);
+      float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
+      float tau_pool = -INFINITY;
+      const int pool_every = p.n_slabs > 32 ? p.n_slabs / 4 : 8;
       const bool no_insert = (p.debug & 2) != 0;
       // inverse norms of the tile's 64 rows: lane l fetches rows 2l, 2l+1 (prefetched one tile ahead),
       // parks them in this warp's shared-memory strip, and every lane reads all 64 by broadcast
@@ -334,7 +368,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         reinterpret_cast<float2*>(nbuf)[lane] = make_float2(nn0, nn1);
         __syncwarp();
         load_norms(t + 1, nn0, nn1);  // prefetch for the next tile
-        float tau = live ? fmaxf(tau_loc, g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
+        if (live && p.m_rank > 0 && ((t - t0) % pool_every) == pool_every - 1) {
+          uint32_t mn = 0xffffffffu;
+          const volatile uint32_t* col = p.gslab + q;
+          for (int sl = 0; sl < p.n_slabs; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
+          if (mn != 0u) tau_pool = fmaxf(tau_pool, unord32(mn));   // 0 = some slab has not reported yet
+        }
+        float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
         if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);  // lands while this tile is processed
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(tfull + as, aph, 5);
@@ -387,6 +427,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
               const uint64_t key = make_key(s, uint32_t(row));
               if (key > root) {
                 root = heap_replace_root(mylist, p.kk, key);
+                if (p.m_rank > 0 && s > tm3) {   // keep this slab's four best scores, publish the m-th
+                  if (s > tm0) { tm3 = tm2; tm2 = tm1; tm1 = tm0; tm0 = s; }
+                  else if (s > tm1) { tm3 = tm2; tm2 = tm1; tm1 = s; }
+                  else if (s > tm2) { tm3 = tm2; tm2 = s; }
+                  else tm3 = s;
+                  const float mth = p.m_rank == 1 ? tm0 : (p.m_rank == 2 ? tm1 : (p.m_rank == 3 ? tm2 : tm3));
+                  if (mth > -INFINITY) *gs = ord32(mth);
+                }
                 if (root) {
                   tau_loc = key_score(root);
                   tau = fmaxf(tau, tau_loc);
@@ -432,10 +480,8 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-static int gcd(int a, int b) { return b ? gcd(b, a % b) : a; }
-
 struct Plan {
-  int nqb, n_tiles, n_slabs, n_stages, grid;
+  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank;
   size_t smem;
 };
 
@@ -451,11 +497,15 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
   pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
   const int g = sm_count();
-  int s = g / gcd(g, pl.nqb);
+  // One item per CTA whenever the query blocks fit: every slab of a query block is then resident at
+  // the same time, which the pooled threshold relies on (and no CTA reloads its A operand).
+  int s = pl.nqb <= g ? g / pl.nqb : 1;
   if (s > pl.n_tiles) s = pl.n_tiles;
   pl.n_slabs = s < 1 ? 1 : s;
   const int items = pl.nqb * pl.n_slabs;
   pl.grid = items < g ? items : g;
+  const int m = (kk + pl.n_slabs - 1) / pl.n_slabs;
+  pl.m_rank = (items <= g && m <= 4) ? m : 0;
   return true;
 }
 
@@ -498,6 +548,8 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.mask = d_mask;
   p.parts = d_parts;
   p.gtau = d_gtau;
+  p.gslab = d_gtau + q_stride;
+  p.m_rank = pl.m_rank;
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -509,7 +561,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_stages = pl.n_stages;
   const char* dbg = getenv("DRS_UMMA_DEBUG");
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
-  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * sizeof(uint32_t), st));
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_slabs) * sizeof(uint32_t), st));
   DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   count_launches(1);
