@@ -24,7 +24,7 @@ constexpr int BM25_TCHUNK = 64;  // query term occurrences whose posting ranges 
 constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
 constexpr int BM25_MERGE_AT = 512;  // survivors that justify a re-sort (warm list)
 
-__global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
+__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
     unsigned long long* __restrict__ gtau) {
@@ -34,6 +34,9 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
   __shared__ long long s_a[BM25_TCHUNK], s_e[BM25_TCHUNK];  // posting ranges of the staged terms in this tile
+  __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
+  __shared__ int s_drow[BM25_TCHUNK], s_sidx[BM25_TCHUNK];   // compacted: dense rows / indices of non-empty posting ranges
+  __shared__ int s_nd, s_ns;
 
   const int T = ix.tile_docs;
   const int tid = threadIdx.x;
@@ -72,86 +75,185 @@ __global__ void __launch_bounds__(BM25_THREADS) bm25_select_kernel(
       const int64_t doc0 = int64_t(j) * T;
       const int64_t rem = ix.n_docs - doc0;
       const int tile_n = rem < int64_t(T) ? int(rem) : T;
-      for (int i = tid; i < T; i += BM25_THREADS) sc[i] = 0.0f;
-      __syncthreads();
-      // ---- accumulate: one term occurrence at a time, in query order -------------------
+      // ---- accumulate ---------------------------------------------------------------------
+      // Order of the fp32 additions into a document's score: the query's head (dense-row) terms first,
+      // in query order, then its postings-list terms in query order.  The order is the same for every
+      // document, so documents with identical (term, impact) patterns still get identical sums.
       // The ranges [a, e) of every staged term inside this tile are fetched by separate threads in one
       // go (term id -> term offset -> tile pointer is a chain of dependent loads; paying it once per
-      // tile instead of once per term keeps the loop below on streaming loads only).
+      // tile instead of once per term keeps the loops below on streaming loads only).
+      bool tile_init = false;   // false: the tile still holds the previous query's scores
       for (int c0 = t0; c0 < t1; c0 += BM25_TCHUNK) {
-      const int nstaged = min(BM25_TCHUNK, t1 - c0);
-      if (tid < nstaged) {
-        const int t = q_terms[c0 + tid];
-        long long a = 0, e = 0;
-        if (t >= 0 && t < ix.n_terms) {  // OOV: contributes nothing
-          const long long base = ix.d_term_offsets[t];
-          const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
-          a = base + tp[0];
-          e = base + tp[1];
+        const int nstaged = min(BM25_TCHUNK, t1 - c0);
+        if (tid < nstaged) {
+          const int t = q_terms[c0 + tid];
+          long long a = 0, e = 0;
+          int slot = -1;
+          if (t >= 0 && t < ix.n_terms) {  // OOV: contributes nothing
+            slot = ix.d_dense_slot ? ix.d_dense_slot[t] : -1;
+            if (slot < 0) {
+              const long long base = ix.d_term_offsets[t];
+              const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+              a = base + tp[0];
+              e = base + tp[1];
+            }
+          }
+          s_a[tid] = a;
+          s_e[tid] = e;
+          s_slot[tid] = slot;
         }
-        s_a[tid] = a;
-        s_e[tid] = e;
+        __syncthreads();
+        if (tid == 0) {  // compact the dense rows / non-empty posting ranges, keeping query order
+          int nd = 0, ns = 0;
+          for (int i = 0; i < nstaged; ++i) {
+            if (s_slot[i] >= 0) s_drow[nd++] = s_slot[i];
+            else if (s_a[i] < s_e[i]) s_sidx[ns++] = i;
+          }
+          s_nd = nd;
+          s_ns = ns;
+        }
+        __syncthreads();
+        const int nd = s_nd, ns = s_ns;
+        // -- pass A: dense rows, up to four fused per sweep; the first sweep also initialises the tile
+        float4* dst = reinterpret_cast<float4*>(sc);
+        for (int g0 = 0; g0 < nd; g0 += 4) {
+          const int ng = min(4, nd - g0);
+          const float4* r0 = reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
+          const float4* r1 = ng > 1 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
+          const float4* r2 = ng > 2 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
+          const float4* r3 = ng > 3 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = tid; i < T / 4; i += 2 * BM25_THREADS) {
+            const int i2 = i + BM25_THREADS;
+            const bool two = i2 < T / 4;
+            const float4 a0 = __ldg(r0 + i), a1 = ng > 1 ? __ldg(r1 + i) : z, a2 = ng > 2 ? __ldg(r2 + i) : z,
+                         a3 = ng > 3 ? __ldg(r3 + i) : z;
+            const float4 b0 = two ? __ldg(r0 + i2) : z, b1 = (two && ng > 1) ? __ldg(r1 + i2) : z,
+                         b2 = (two && ng > 2) ? __ldg(r2 + i2) : z, b3 = (two && ng > 3) ? __ldg(r3 + i2) : z;
+            float4 x = tile_init ? dst[i] : z;
+            x.x += a0.x; x.y += a0.y; x.z += a0.z; x.w += a0.w;
+            if (ng > 1) { x.x += a1.x; x.y += a1.y; x.z += a1.z; x.w += a1.w; }
+            if (ng > 2) { x.x += a2.x; x.y += a2.y; x.z += a2.z; x.w += a2.w; }
+            if (ng > 3) { x.x += a3.x; x.y += a3.y; x.z += a3.z; x.w += a3.w; }
+            dst[i] = x;
+            if (two) {
+              float4 y = tile_init ? dst[i2] : z;
+              y.x += b0.x; y.y += b0.y; y.z += b0.z; y.w += b0.w;
+              if (ng > 1) { y.x += b1.x; y.y += b1.y; y.z += b1.z; y.w += b1.w; }
+              if (ng > 2) { y.x += b2.x; y.y += b2.y; y.z += b2.z; y.w += b2.w; }
+              if (ng > 3) { y.x += b3.x; y.y += b3.y; y.z += b3.z; y.w += b3.w; }
+              dst[i2] = y;
+            }
+          }
+          tile_init = true;
+          __syncthreads();
+        }
+        if (!tile_init) {
+          for (int i = tid; i < T / 4; i += BM25_THREADS) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          tile_init = true;
+          __syncthreads();
+        }
+        // -- pass B: postings-list terms, one per barrier; the first 4 postings per thread of the NEXT
+        // term are fetched before the barrier of the current one
+        const uint32_t d0u = uint32_t(doc0);  // tile-local index = document id - d0u
+        uint4 pd = make_uint4(0, 0, 0, 0);
+        float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto prefetch = [&](int k) {   // first vector group of sparse term k (if this thread has one)
+          if (k < ns) {
+            const int64_t a = s_a[s_sidx[k]], e = s_e[s_sidx[k]];
+            int64_t a4 = (a + 3) & ~int64_t(3);
+            if (a4 > e) a4 = e;
+            if (tid < ((e - a4) >> 2)) {
+              pd = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + a4) + tid);
+              pi = __ldg(reinterpret_cast<const float4*>(ix.d_post_impact + a4) + tid);
+            }
+          }
+        };
+        prefetch(0);
+        for (int k = 0; k < ns; ++k) {
+          const int64_t a = s_a[s_sidx[k]], e = s_e[s_sidx[k]];
+          // head (to 16-byte alignment), vector body (4 postings per thread per load), tail.  Inside one
+          // term every document occurs once, so the read-modify-writes of a batch never alias: all loads
+          // are issued before the adds and stores.
+          int64_t a4 = (a + 3) & ~int64_t(3);
+          if (a4 > e) a4 = e;
+          const int64_t nvec = (e - a4) >> 2;
+          const uint4 d0 = pd;
+          const float4 i0 = pi;
+          const bool have0 = tid < nvec;
+          // tail / head / further groups of this term, then the next term's first group
+          uint32_t hd = 0, td = 0;
+          float hi = 0.f, tl = 0.f;
+          const bool haveh = a + tid < a4;
+          const int64_t ts = a4 + (nvec << 2);
+          const bool havet = ts + tid < e;
+          if (haveh) {
+            hd = __ldg(ix.d_post_doc + a + tid);
+            hi = __ldg(ix.d_post_impact + a + tid);
+          }
+          if (havet) {
+            td = __ldg(ix.d_post_doc + ts + tid);
+            tl = __ldg(ix.d_post_impact + ts + tid);
+          }
+          prefetch(k + 1);
+          if (have0) {
+            const float v0 = sc[d0.x - d0u], v1 = sc[d0.y - d0u], v2 = sc[d0.z - d0u], v3 = sc[d0.w - d0u];
+            sc[d0.x - d0u] = v0 + i0.x;
+            sc[d0.y - d0u] = v1 + i0.y;
+            sc[d0.z - d0u] = v2 + i0.z;
+            sc[d0.w - d0u] = v3 + i0.w;
+          }
+          const uint4* dv = reinterpret_cast<const uint4*>(ix.d_post_doc + a4);
+          const float4* iv = reinterpret_cast<const float4*>(ix.d_post_impact + a4);
+          for (int64_t v = tid + BM25_THREADS; v < nvec; v += BM25_THREADS) {
+            const uint4 d1 = __ldg(dv + v);
+            const float4 i1 = __ldg(iv + v);
+            const float v0 = sc[d1.x - d0u], v1 = sc[d1.y - d0u], v2 = sc[d1.z - d0u], v3 = sc[d1.w - d0u];
+            sc[d1.x - d0u] = v0 + i1.x;
+            sc[d1.y - d0u] = v1 + i1.y;
+            sc[d1.z - d0u] = v2 + i1.z;
+            sc[d1.w - d0u] = v3 + i1.w;
+          }
+          if (haveh) sc[hd - d0u] += hi;
+          if (havet) sc[td - d0u] += tl;
+          __syncthreads();
+        }
+        __syncthreads();  // the staging arrays may be rewritten
       }
-      __syncthreads();
-      for (int ti = 0; ti < nstaged; ++ti) {
-        const int64_t a = s_a[ti], e = s_e[ti];
-        if (a >= e) continue;  // block-uniform: nothing written, no barrier needed
-        // head (to 16-byte alignment), vector body (4 postings per thread per load), tail
-        int64_t a4 = (a + 3) & ~int64_t(3);
-        if (a4 > e) a4 = e;
-        if (a + tid < a4) sc[__ldg(ix.d_post_doc + a + tid) - doc0] += __ldg(ix.d_post_impact + a + tid);
-        const int64_t nvec = (e - a4) >> 2;
-        const uint4* dv = reinterpret_cast<const uint4*>(ix.d_post_doc + a4);
-        const float4* iv = reinterpret_cast<const float4*>(ix.d_post_impact + a4);
-        int64_t v = tid;
-        for (; v + BM25_THREADS < nvec; v += 2 * BM25_THREADS) {
-          const uint4 d0 = __ldg(dv + v), d1 = __ldg(dv + v + BM25_THREADS);
-          const float4 i0 = __ldg(iv + v), i1 = __ldg(iv + v + BM25_THREADS);
-          sc[d0.x - doc0] += i0.x;
-          sc[d0.y - doc0] += i0.y;
-          sc[d0.z - doc0] += i0.z;
-          sc[d0.w - doc0] += i0.w;
-          sc[d1.x - doc0] += i1.x;
-          sc[d1.y - doc0] += i1.y;
-          sc[d1.z - doc0] += i1.z;
-          sc[d1.w - doc0] += i1.w;
-        }
-        for (; v < nvec; v += BM25_THREADS) {
-          const uint4 d0 = __ldg(dv + v);
-          const float4 i0 = __ldg(iv + v);
-          sc[d0.x - doc0] += i0.x;
-          sc[d0.y - doc0] += i0.y;
-          sc[d0.z - doc0] += i0.z;
-          sc[d0.w - doc0] += i0.w;
-        }
-        const int64_t ts = a4 + (nvec << 2);
-        if (ts + tid < e) sc[__ldg(ix.d_post_doc + ts + tid) - doc0] += __ldg(ix.d_post_impact + ts + tid);
+      if (!tile_init) {   // query without terms: every score is 0
+        for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
       }
-      __syncthreads();  // ranges may be restaged
-      }
       // ---- scan the tile, highest document first -----------------------------------------
-      for (int seg = 0; seg < T; seg += BM25_SEG) {
+      // While this CTA has no threshold yet for the query (cold list, nothing published by other CTAs)
+      // only 256 documents are scanned before the first merge, so the first sort is small.
+      int done = 0;
+      while (done < T) {
         const unsigned long long tau = s_tau;
-#pragma unroll
-        for (int u = 0; u < BM25_SEG / BM25_THREADS; ++u) {
-          const int dl = T - 1 - (seg + u * BM25_THREADS + tid);
+        const bool cold = (tau == 0);
+        const float tau_s = cold ? -INFINITY : key_score(tau);
+        const int step = cold ? BM25_THREADS : BM25_SEG;
+        for (int u = 0; u < step; u += BM25_THREADS) {
+          const int dl = T - 1 - (done + u + tid);
           if (dl < tile_n && dl >= 0) {
-            const uint64_t key = make_key(sc[dl], uint32_t(doc0 + dl));
-            if (key > tau) {
-              const int pos = atomicAdd(&s_cnt, 1);
-              if (pos < cap) mbuf[kk + pos] = key;
+            const float s = sc[dl];
+            if (s >= tau_s) {
+              const uint64_t key = make_key(s, uint32_t(doc0 + dl));
+              if (key > tau) {
+                const int pos = atomicAdd(&s_cnt, 1);
+                if (pos < cap) mbuf[kk + pos] = key;
+              }
             }
           }
         }
+        done += step;
         __syncthreads();
         // Merge (sort list + survivors, tighten the threshold) when the append area could overflow in
         // the next segment, when enough survivors piled up that a tighter threshold pays for the
         // sort, as soon as a cold list can be filled, and at the very end of this CTA's tiles.
-        const bool last = (seg + BM25_SEG >= T) && (j == tile_lo);
+        const bool last = (done >= T) && (j == tile_lo);
         const int cnt = s_cnt;
-        if (cnt > 0 && (last || cnt > cap - BM25_SEG || cnt >= BM25_MERGE_AT || (mbuf[kk - 1] == 0 && cnt >= kk)))
-          merge(q);
+        if (cnt > 0 && (last || cnt > cap - BM25_SEG || cnt >= BM25_MERGE_AT || (cold && cnt >= kk))) merge(q);
       }
     }
     for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];

@@ -52,6 +52,7 @@ class Bm25DeviceIndex:
         self.row_offset = 0                        # global row of local document 0 (sharded corpora)
         self.n_docs_global = 0
         self.total_tokens = 0
+        self.n_dense = 0                           # head terms that also have a dense impact row
         self.t: Dict[str, torch.Tensor] = {}       # device tensors
         self._struct = None
 
@@ -63,7 +64,8 @@ class Bm25DeviceIndex:
     # -----------------------------------------------------------------------------
     @classmethod
     def from_token_ids(cls, doc_offsets, tokens, vocab_size: int, k1=1.5, b=0.75, epsilon=0.25,
-                       device="cuda", tile_docs: int | None = None, build_device=None, group=None):
+                       device="cuda", tile_docs: int | None = None, build_device=None, group=None,
+                       dense_frac: float = 0.25, max_dense_terms: int = 64):
         """``doc_offsets`` int64 [N+1], ``tokens`` int32 [total] (term ids in [0, vocab_size)).
 
         ``group``: a ``torch.distributed`` process group (or ``True`` for the default group) when
@@ -163,7 +165,25 @@ class Bm25DeviceIndex:
         tile_ptr = torch.zeros(self.n_terms, self.n_tiles + 1, dtype=torch.int64, device=build_device)
         torch.cumsum(cnt, 1, out=tile_ptr[:, 1:])
         del cnt
+        # dense impact rows for the head terms (local df >= dense_frac * n): vector-add path
+        n_pad = self.n_tiles * self.tile_docs
+        dense_slot = torch.full((self.n_terms,), -1, dtype=torch.int32, device=build_device)
+        heavy = torch.nonzero(df >= max(1.0, dense_frac * n)).flatten()
+        if heavy.numel() > max_dense_terms:
+            heavy = heavy[torch.argsort(df[heavy], descending=True)[:max_dense_terms]]
+        dense_impact = torch.zeros(max(int(heavy.numel()), 1), n_pad, dtype=torch.float32, device=build_device)
+        if heavy.numel() and dense_frac > 0:
+            dense_slot[heavy] = torch.arange(heavy.numel(), dtype=torch.int32, device=build_device)
+            slot_of_post = dense_slot[post_term]
+            sel = slot_of_post >= 0
+            dense_impact[slot_of_post[sel].long(), post_doc[sel]] = impact[sel]
+            del slot_of_post, sel
+        else:
+            dense_slot.fill_(-1)
+        self.n_dense = int((dense_slot >= 0).sum())
         self.t = {
+            "dense_slot": dense_slot.to(device),
+            "dense_impact": dense_impact.to(device),
             "term_offsets": term_offsets.to(device),
             "post_doc": post_doc.to(torch.int32).to(device),      # bit pattern of u32 (n < 2^31 enforced below)
             "post_impact": impact.to(device),
@@ -214,6 +234,9 @@ class Bm25DeviceIndex:
             s.d_idf = t["idf"].data_ptr()
             s.d_doc_kd = t["doc_kd"].data_ptr()
             s.k1_plus_1 = self.k1 + 1
+            s.d_dense_slot = t["dense_slot"].data_ptr()
+            s.d_dense_impact = t["dense_impact"].data_ptr()
+            s.dense_stride = self.n_tiles * self.tile_docs
             self._struct = s
         return self._struct
 

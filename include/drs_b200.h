@@ -101,6 +101,12 @@ typedef struct drs_bm25_index {
   const double* d_idf;          /* [V] idf incl. the epsilon floor (bm25 `idf` dict)     */
   const double* d_doc_kd;       /* [N] k1*(1-b+b*doc_len/avgdl), fp64, reference op order */
   double k1_plus_1;             /* k1 + 1                                                */
+  /* Head terms (present in a large fraction of the documents) additionally carry a DENSE row of
+     per-document impacts: adding a row is a vector add (4 bytes/document, no scatter).  The
+     values are the same fp32 impacts, 0 where the term is absent, so scores are unchanged.    */
+  const int32_t* d_dense_slot;  /* [V] row of the term in d_dense_impact, -1 = sparse only; may be NULL */
+  const float* d_dense_impact;  /* [n_dense, dense_stride]                               */
+  int64_t dense_stride;         /* n_tiles * tile_docs (rows are zero padded)            */
 } drs_bm25_index;
 
 /* ---------------------------------------------------------------------------------

@@ -99,3 +99,21 @@ def test_tile_size_choice():
     assert choose_tile_docs(100_000) == 1024
     assert choose_tile_docs(1_000_000) == 8192
     assert choose_tile_docs(10_000_000) == 8192
+
+
+def test_dense_head_term_rows_match_postings():
+    offs, toks = synth.zipf_docs(3000, vocab=60, seed=77, len_min=5, len_max=40)
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, 60, device="cpu", tile_docs=256, dense_frac=0.25)
+    assert ix.n_dense > 0
+    slot = ix.t["dense_slot"].numpy()
+    df = np.diff(ix.t["term_offsets"].numpy())
+    assert ((slot >= 0) == (df >= 0.25 * 3000)).all()
+    dense = ix.t["dense_impact"].numpy()
+    assert dense.shape[1] == ix.n_tiles * ix.tile_docs
+    to, pd, pi = ix.t["term_offsets"].numpy(), ix.t["post_doc"].numpy(), ix.t["post_impact"].numpy()
+    for t in np.flatnonzero(slot >= 0):
+        row = np.zeros(dense.shape[1], dtype=np.float32)
+        row[pd[to[t]:to[t + 1]]] = pi[to[t]:to[t + 1]]
+        assert np.array_equal(dense[slot[t]], row)
+    off = Bm25DeviceIndex.from_token_ids(offs, toks, 60, device="cpu", tile_docs=256, dense_frac=0.0)
+    assert off.n_dense == 0

@@ -141,8 +141,9 @@ def test_dense_umma_mask_and_auto_dispatch():
 # ----------------------------------------------------------------------------------------------
 # BM25
 # ----------------------------------------------------------------------------------------------
-def _check_bm25(offs, toks, vocab, queries, kprime, k1=1.5, b=0.75, tile_docs=None):
-    ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, k1=k1, b=b, device=DEV, tile_docs=tile_docs)
+def _check_bm25(offs, toks, vocab, queries, kprime, k1=1.5, b=0.75, tile_docs=None, dense_frac=0.25):
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, k1=k1, b=b, device=DEV, tile_docs=tile_docs,
+                                        dense_frac=dense_frac)
     orc = obm25.Bm25Csr(offs, toks, vocab, k1=k1, b=b)
     qt, qo = ix.encode_queries(queries)
     sc, ids = _lib.bm25_topk(ix.struct(), qt.to(DEV), qo.to(DEV), len(queries), kprime)
@@ -174,6 +175,7 @@ def test_bm25_shapes(n, vocab, tile):
            np.array([vocab - 1] * 5, dtype=np.int32), np.array([0, 0, 1, 0], dtype=np.int32)]  # rare / repeated head terms
     _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile)
     _check_bm25(offs, toks, vocab, qs[:6], 20, k1=1.2, b=0.3, tile_docs=tile)
+    _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile, dense_frac=0.0)     # postings-only path
 
 
 def test_bm25_negative_idf_floor_branch():
