@@ -37,6 +37,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
   __shared__ int s_drow[BM25_TCHUNK], s_sidx[BM25_TCHUNK];   // compacted: dense rows / indices of non-empty posting ranges
   __shared__ int s_nd, s_ns;
+  __shared__ int s_term[BM25_TCHUNK];
+  __shared__ long long s_base[BM25_TCHUNK];
 
   const int T = ix.tile_docs;
   const int tid = threadIdx.x;
@@ -62,8 +64,42 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     __syncthreads();
   };
 
+  // Term metadata of up to BM25_TCHUNK query-term occurrences: term id, dense row (or -1), start of the
+  // postings list (or -1 when the term is dense, out of vocabulary, or absent).  Tile independent, so a
+  // query that fits in one chunk stages it ONCE per (CTA, query) instead of once per tile.
+  auto stage_terms = [&](int c0, int nstaged) {
+    __syncthreads();
+    if (tid < nstaged) {
+      const int t = q_terms[c0 + tid];
+      int slot = -1;
+      long long base = -1;
+      if (t >= 0 && t < ix.n_terms) {  // OOV: contributes nothing
+        slot = ix.d_dense_slot ? ix.d_dense_slot[t] : -1;
+        if (slot < 0) base = ix.d_term_offsets[t];
+      }
+      s_term[tid] = t;
+      s_slot[tid] = slot;
+      s_base[tid] = base;
+    }
+    __syncthreads();
+    if (tid < 32) {   // warp 0 compacts the dense rows, keeping query order
+      int nd = 0;
+      for (int b0 = 0; b0 < nstaged; b0 += 32) {
+        const int i = b0 + tid;
+        const bool f = i < nstaged && s_slot[i] >= 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (f) s_drow[nd + __popc(m & ((1u << tid) - 1u))] = s_slot[i];
+        nd += __popc(m);
+      }
+      if (tid == 0) s_nd = nd;
+    }
+    __syncthreads();
+  };
+
   for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
+    const bool one_chunk = (t1 - t0) <= BM25_TCHUNK;
+    if (one_chunk) stage_terms(t0, t1 - t0);
     for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
     if (tid == 0) {
       s_cnt = 0;
@@ -85,32 +121,30 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       bool tile_init = false;   // false: the tile still holds the previous query's scores
       for (int c0 = t0; c0 < t1; c0 += BM25_TCHUNK) {
         const int nstaged = min(BM25_TCHUNK, t1 - c0);
+        if (!one_chunk) stage_terms(c0, nstaged);   // long queries: term metadata is restaged per tile
+        // this tile's posting ranges of the postings-list terms (one dependent load per term)
         if (tid < nstaged) {
-          const int t = q_terms[c0 + tid];
+          const long long base = s_base[tid];
           long long a = 0, e = 0;
-          int slot = -1;
-          if (t >= 0 && t < ix.n_terms) {  // OOV: contributes nothing
-            slot = ix.d_dense_slot ? ix.d_dense_slot[t] : -1;
-            if (slot < 0) {
-              const long long base = ix.d_term_offsets[t];
-              const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
-              a = base + tp[0];
-              e = base + tp[1];
-            }
+          if (base >= 0) {
+            const uint32_t* tp = ix.d_tile_ptr + size_t(s_term[tid]) * (ix.n_tiles + 1) + j;
+            a = base + tp[0];
+            e = base + tp[1];
           }
           s_a[tid] = a;
           s_e[tid] = e;
-          s_slot[tid] = slot;
         }
         __syncthreads();
-        if (tid == 0) {  // compact the dense rows / non-empty posting ranges, keeping query order
-          int nd = 0, ns = 0;
-          for (int i = 0; i < nstaged; ++i) {
-            if (s_slot[i] >= 0) s_drow[nd++] = s_slot[i];
-            else if (s_a[i] < s_e[i]) s_sidx[ns++] = i;
+        if (tid < 32) {   // warp 0 compacts the indices of the non-empty ranges, keeping query order
+          int ns = 0;
+          for (int b0 = 0; b0 < nstaged; b0 += 32) {
+            const int i = b0 + tid;
+            const bool f = i < nstaged && s_a[i] < s_e[i];
+            const unsigned m = __ballot_sync(0xffffffffu, f);
+            if (f) s_sidx[ns + __popc(m & ((1u << tid) - 1u))] = i;
+            ns += __popc(m);
           }
-          s_nd = nd;
-          s_ns = ns;
+          if (tid == 0) s_ns = ns;
         }
         __syncthreads();
         const int nd = s_nd, ns = s_ns;
