@@ -55,7 +55,8 @@ struct Params {
   int64_t n_rows;
   int n_queries, nqb, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
   uint32_t debug;
-  int m_rank;      // ceil(kk / n_slabs) if <= 4 and all slabs run concurrently, else 0 (pooling off)
+  int m_rank;      // ceil(kk / (n_groups*n_slabs)) if <= 4 and all slabs run concurrently, else 0 (pooling off)
+  int n_groups;    // epilogue warp groups (candidate heaps per query per CTA): 2, or 1 for large kk
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
   // carve: [ring | lists | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);
-  uint64_t* bars = lists + 2 * size_t(p.kk) * BLOCK_M;
+  uint64_t* bars = lists + size_t(p.n_groups) * p.kk * BLOCK_M;
   uint64_t* full = bars;
   uint64_t* empty = bars + p.n_stages;
   uint64_t* tfull = bars + 2 * p.n_stages;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
     mbar_init(tfull + 1, 1);
     mbar_init(tempty + 0, 4);
     mbar_init(tempty + 1, 4);
-    mbar_init(a_ready, 8);
+    mbar_init(a_ready, 4 * p.n_groups);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + 4 * p.n_groups) {
     // ===================================================================== A loader + epilogue
     // Two epilogue groups of four warps.  Group g owns accumulator stage g and therefore every other
     // tile, so each group has TWO tile-times of tensor work to drain one tile; each keeps its own
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
     const int grp = (warp - 4) >> 2;         // 0 or 1
     const int L = ew * 32 + lane;            // TMEM lane == query within the block
     const uint32_t lane_addr = uint32_t(ew * 32) << 16;
+    const int ng = p.n_groups;               // 2 normally; 1 when two heaps per query would not fit in smem
     const uint32_t mylist = smem_u32(lists) + uint32_t(grp * p.kk * BLOCK_M + L) * 8;  // my heap's slot 0
     float* norm_strip = norm_strips + (warp - 4) * 2 * TILE_N;
     uint32_t it = 0;                         // tiles issued so far (both groups), mirrors the MMA warp
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       const int q = qb * BLOCK_M + L;
       const bool live = q < p.n_queries;
       const float* qrow = p.queries + size_t(live ? q : 0) * p.dim;
-      for (int c0 = grp * 32; c0 < p.dim / 2; c0 += 64) {   // the two groups interleave 32-column chunks
+      for (int c0 = grp * 32; c0 < p.dim / 2; c0 += 32 * ng) {   // the groups interleave 32-column chunks
         uint32_t v[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -353,11 +355,11 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       // gslab[slab][q].  If every slab has m rows scoring >= x, the corpus has >= kk such rows, so
       // x = min over slabs is a valid lower bound on the global kk-th best -- and a far tighter one than
       // any single slab's own kk-th best while all the lists are still warming up.
-      const int vslab = slab * 2 + grp;
+      const int vslab = slab * ng + grp;
       volatile uint32_t* gs = p.gslab + size_t(vslab) * p.q_stride + (live ? q : 0);
       float tm0 = -INFINITY, tm1 = -INFINITY, tm2 = -INFINITY, tm3 = -INFINITY;
       float tau_pool = -INFINITY;
-      const int n_vslabs = 2 * p.n_slabs;
+      const int n_vslabs = ng * p.n_slabs;
       const int pool_every = n_vslabs > 32 ? n_vslabs / 4 : 8;
       const bool no_insert = (p.debug & 2) != 0;
       // inverse norms of the tile's 64 rows: lane l fetches rows 2l, 2l+1 (prefetched one tile ahead),
@@ -368,15 +370,15 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         n1 = (t < t1 && r + 1 < p.n_rows) ? __ldg(p.inv_norm + r + 1) : 0.f;
       };
       float nn0, nn1;
-      const int t_first = t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of this item
+      const int t_first = (ng == 1) ? t0 : t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of this item
       load_norms(t_first, nn0, nn1);
       int nt = 0;
-      for (int t = t_first; t < t1; t += 2, ++nt) {
+      for (int t = t_first; t < t1; t += ng, ++nt) {
         const uint32_t itt = it + uint32_t(t - t0);      // this tile's global sequence number (parity == grp)
-        float* nbuf = norm_strip + ((itt >> 1) & 1) * TILE_N;
+        float* nbuf = norm_strip + (nt & 1) * TILE_N;
         reinterpret_cast<float2*>(nbuf)[lane] = make_float2(nn0, nn1);
         __syncwarp();
-        load_norms(t + 2, nn0, nn1);  // prefetch for my next tile
+        load_norms(t + ng, nn0, nn1);  // prefetch for my next tile
         // refreshed before each of the first tiles (thresholds move fastest while the heaps fill), then periodically
         if (live && p.m_rank > 0 && (nt < 12 || (nt % pool_every) == pool_every - 1)) {
           uint32_t mn = 0xffffffffu;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         }
         float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
         if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);  // lands while this tile is processed
-        const uint32_t as = uint32_t(grp), aph = (itt >> 1) & 1;
+        const uint32_t as = itt & 1u, aph = (itt >> 1) & 1;   // with two groups as == grp
         mbar_wait(tfull + as, aph, 5);
         tc_fence_after();
         uint32_t acc0[32], acc1[32];
@@ -492,14 +494,20 @@ static EncodeTiledFn encode_tiled() {
 }
 
 struct Plan {
-  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank;
+  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups;
   size_t smem;
 };
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
   if (dim % STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
   if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
-  const size_t fixed = 1024 /*align*/ + 2 * size_t(kk) * BLOCK_M * 8 + 6144 /*barriers, tmem slot, norm strips*/;
+  // two candidate heaps per query (one per epilogue group) when they leave room for a >= 6-stage ring
+  size_t fixed = 1024 /*align*/ + 2 * size_t(kk) * BLOCK_M * 8 + 6144 /*barriers, tmem slot, norm strips*/;
+  pl.n_groups = 2;
+  if (fixed + 6 * size_t(STAGE_BYTES) > SMEM_LIMIT) {
+    fixed -= size_t(kk) * BLOCK_M * 8;
+    pl.n_groups = 1;
+  }
   if (fixed + size_t(MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
   if (ns > 12) ns = 12;
@@ -515,7 +523,7 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   pl.n_slabs = s < 1 ? 1 : s;
   const int items = pl.nqb * pl.n_slabs;
   pl.grid = items < g ? items : g;
-  const int m = (kk + 2 * pl.n_slabs - 1) / (2 * pl.n_slabs);   // two candidate heaps (virtual slabs) per CTA
+  const int m = (kk + pl.n_groups * pl.n_slabs - 1) / (pl.n_groups * pl.n_slabs);   // heaps == virtual slabs
   pl.m_rank = (items <= g && m <= 4) ? m : 0;
   return true;
 }
@@ -531,7 +539,7 @@ int dense_umma_query_mode() { return DRS_QMODE_BF16_RAW; }
 
 int dense_umma_parts(int n_queries, int64_t n_rows, int dim, int kk) {
   umma::Plan pl;
-  return umma::make_plan(n_queries, n_rows, dim, kk, pl) ? 2 * pl.n_slabs : 0;
+  return umma::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs : 0;
 }
 
 int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
@@ -561,6 +569,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.gtau = d_gtau;
   p.gslab = d_gtau + q_stride;
   p.m_rank = pl.m_rank;
+  p.n_groups = pl.n_groups;
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -572,7 +581,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_stages = pl.n_stages;
   const char* dbg = getenv("DRS_UMMA_DEBUG");
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
-  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + 2 * pl.n_slabs) * sizeof(uint32_t), st));
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
   DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
   dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   count_launches(1);
