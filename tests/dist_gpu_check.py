@@ -1,0 +1,73 @@
+"""Multi-GPU parity check, launched with torchrun (one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 \
+        tests/dist_gpu_check.py
+
+Every rank builds the SAME small corpus, keeps its row shard, and runs the sharded hybrid search (local
+top-k' -> all-gather of candidate lists over NCCL -> merge -> fusion).  Rank 0 also runs the unsharded path on
+the whole corpus and the CPU oracle; all three must agree (ids exact, RRF scores exact)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from domain_rag_system_b200 import _lib, synth  # noqa: E402
+from domain_rag_system_b200.dist import ShardedHybridSearcher, shard_bounds  # noqa: E402
+from domain_rag_system_b200.indexing.bm25_index import Bm25DeviceIndex  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n, vocab, nq, top_k = 60_000, 3000, 200, 10
+    emb = synth.unit_embeddings(n, seed=1234, dup_frac=0.001)
+    offs, toks = synth.zipf_docs(n, vocab=vocab, seed=2025)
+    qv = synth.query_embeddings(nq, corpus=emb, seed=4321)
+    qt = synth.zipf_queries(nq, offs, toks, vocab=vocab, seed=777)
+
+    lo, hi = shard_bounds(n, world, rank)
+    rows = emb[lo:hi].to(dev)
+    inv = _lib.row_inv_norms(rows)
+    ix = Bm25DeviceIndex.from_token_ids(offs[lo:hi + 1] - offs[lo], toks[offs[lo]:offs[hi]], vocab, device=dev,
+                                        build_device=dev, group=True)
+    q_terms, q_offs = ix.encode_queries(qt)
+    searcher = ShardedHybridSearcher(rows, inv, ix, row_offset=lo)
+    ok = True
+    for method in ("rrf", "weighted"):
+        ids, sc = searcher.search_batch(qv.to(dev), q_terms.to(dev), q_offs.to(dev), top_k=top_k, fusion_method=method)
+        torch.cuda.synchronize()
+        if rank == 0:
+            full_rows = emb.to(dev)
+            full = ShardedHybridSearcher(full_rows, _lib.row_inv_norms(full_rows),
+                                         Bm25DeviceIndex.from_token_ids(offs, toks, vocab, device=dev, build_device=dev),
+                                         row_offset=0)
+            full.world = 1
+            ids1, sc1 = full.search_batch(qv.to(dev), q_terms.to(dev), q_offs.to(dev), top_k=top_k, fusion_method=method)
+            same_ids = bool(torch.equal(ids, ids1))
+            same_sc = bool(torch.equal(sc, sc1)) if method == "rrf" else bool(torch.allclose(sc, sc1, rtol=1e-6))
+            print(f"[dist check] world={world} {method}: ids equal to single-GPU = {same_ids}, scores = {same_sc}")
+            ok = ok and same_ids and same_sc
+    # every rank holds the same answer
+    t = torch.tensor([int(ids.sum().item())], device=dev)
+    lst = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(lst, t)
+    if rank == 0:
+        agree = all(int(x) == int(lst[0]) for x in lst)
+        print(f"[dist check] all ranks agree: {agree}")
+        ok = ok and agree
+        print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED")
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -393,3 +393,17 @@ def test_search_batch_equals_per_query_search(tmp_path):
             assert [r["score"] for r in one] == sc[i][: len(one)].tolist()
             rer = rr.rerank(t, one, top_k=5)
             assert [r["metadata"]["row"] for r in rer] == out["rerank_ids"][i].cpu().tolist()
+
+
+def test_multi_gpu_sharded_search_matches_single_gpu():
+    """Needs >= 2 GPUs (skipped otherwise): row-sharded search over NCCL equals the unsharded path."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
