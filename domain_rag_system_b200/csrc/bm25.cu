@@ -22,7 +22,8 @@ constexpr int BM25_THREADS = 256;
 constexpr int BM25_MBUF = 2048;  // merge buffer (u64 keys): list + candidate append area
 constexpr int BM25_TCHUNK = 64;  // query term occurrences whose posting ranges are staged per tile at once
 constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
-constexpr int BM25_MERGE_AT = 512;  // survivors that justify a re-sort (warm list)
+constexpr int BM25_MERGE_AT = 192;  // survivors that justify a re-sort (warm list): list + survivors fit a 256-sort
+constexpr int BM25_COLD_STEP = 128; // documents scanned before the first merge of a cold list
 
 __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
@@ -266,16 +267,23 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         const unsigned long long tau = s_tau;
         const bool cold = (tau == 0);
         const float tau_s = cold ? -INFINITY : key_score(tau);
-        const int step = cold ? BM25_THREADS : BM25_SEG;
-        for (int u = 0; u < step; u += BM25_THREADS) {
-          const int dl = T - 1 - (done + u + tid);
-          if (dl < tile_n && dl >= 0) {
-            const float s = sc[dl];
-            if (s >= tau_s) {
-              const uint64_t key = make_key(s, uint32_t(doc0 + dl));
-              if (key > tau) {
-                const int pos = atomicAdd(&s_cnt, 1);
-                if (pos < cap) mbuf[kk + pos] = key;
+        const int step = cold ? BM25_COLD_STEP : BM25_SEG;
+        // four consecutive documents per thread: one 16-byte shared load and a max test reject almost
+        // every group once the threshold is warm
+        if (4 * tid < step && done + 4 * tid < T) {
+          const int hi = T - 1 - done - 4 * tid;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
+          const float4 v = *reinterpret_cast<const float4*>(sc + hi - 3);
+          if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tau_s) {
+            const float vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int dl = hi - u;
+              if (vs[u] >= tau_s && dl < tile_n) {
+                const uint64_t key = make_key(vs[u], uint32_t(doc0 + dl));
+                if (key > tau) {
+                  const int pos = atomicAdd(&s_cnt, 1);
+                  if (pos < cap) mbuf[kk + pos] = key;
+                }
               }
             }
           }
