@@ -416,10 +416,35 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
           m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
         }
         if (no_insert) m0 = m1 = 0;
-        // ---- pass 2, rare and rolled: for every column some lane flagged, all lanes re-read that one
-        // accumulator column from TMEM (the load is warp-collective) and the flagged lanes insert.
+        // ---- pass 2, rare and rolled.  2a: for every column some lane flagged, all lanes re-read that one
+        // accumulator column from TMEM (the load is warp-collective); a flagged lane only STASHES its score
+        // (four register slots).  The accumulator stage is then handed back to the MMA warp, and the heap
+        // work (2b) -- the expensive part -- runs off the tensor pipe's critical path.
+        auto insert = [&](float s, int j) {
+          const int64_t row = int64_t(t) * TILE_N + j;
+          if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
+            const uint64_t key = make_key(s, uint32_t(row));
+            if (key > root) {
+              root = heap_replace_root(mylist, p.kk, key);
+              if (p.m_rank > 0 && s > tm3) {   // keep this slab's four best scores, publish the m-th
+                if (s > tm0) { tm3 = tm2; tm2 = tm1; tm1 = tm0; tm0 = s; }
+                else if (s > tm1) { tm3 = tm2; tm2 = tm1; tm1 = s; }
+                else if (s > tm2) { tm3 = tm2; tm2 = s; }
+                else tm3 = s;
+                const float mth = p.m_rank == 1 ? tm0 : (p.m_rank == 2 ? tm1 : (p.m_rank == 3 ? tm2 : tm3));
+                if (mth > -INFINITY) *gs = ord32(mth);
+              }
+              if (root) {
+                tau_loc = key_score(root);
+                tau = fmaxf(tau, tau_loc);
+                atomicMax(gt, ord32(tau_loc));
+              }
+            }
+          }
+        };
         uint32_t u0 = __reduce_or_sync(0xffffffffu, m0), u1 = __reduce_or_sync(0xffffffffu, m1);
-        const int64_t row0 = int64_t(t) * TILE_N;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nst = 0;
         while (u0 | u1) {
           int j;
           if (u0) {
@@ -434,31 +459,22 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
           const bool mine = (((j < 32) ? (m0 >> j) : (m1 >> (j - 32))) & 1u) != 0;
           if (mine) {
             const float s = __uint_as_float(v) * nbuf[j];
-            const int64_t row = row0 + j;
-            if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
-              const uint64_t key = make_key(s, uint32_t(row));
-              if (key > root) {
-                root = heap_replace_root(mylist, p.kk, key);
-                if (p.m_rank > 0 && s > tm3) {   // keep this slab's four best scores, publish the m-th
-                  if (s > tm0) { tm3 = tm2; tm2 = tm1; tm1 = tm0; tm0 = s; }
-                  else if (s > tm1) { tm3 = tm2; tm2 = tm1; tm1 = s; }
-                  else if (s > tm2) { tm3 = tm2; tm2 = s; }
-                  else tm3 = s;
-                  const float mth = p.m_rank == 1 ? tm0 : (p.m_rank == 2 ? tm1 : (p.m_rank == 3 ? tm2 : tm3));
-                  if (mth > -INFINITY) *gs = ord32(mth);
-                }
-                if (root) {
-                  tau_loc = key_score(root);
-                  tau = fmaxf(tau, tau_loc);
-                  atomicMax(gt, ord32(tau_loc));
-                }
-              }
-            }
+            if (nst == 0) { s0 = s; j0 = j; }
+            else if (nst == 1) { s1 = s; j1 = j; }
+            else if (nst == 2) { s2 = s; j2 = j; }
+            else if (nst == 3) { s3 = s; j3 = j; }
+            else insert(s, j);                 // stash full (warm-up tiles only): insert in place
+            ++nst;
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty + as);  // accumulator stage may be overwritten
+        // ---- 2b
+        if (nst > 0) insert(s0, j0);
+        if (nst > 1) insert(s1, j1);
+        if (nst > 2) insert(s2, j2);
+        if (nst > 3) insert(s3, j3);
       }
       it += uint32_t(t1 - t0);
       // ---- hand the list over
