@@ -29,10 +29,10 @@ namespace umma {
 
 constexpr int BLOCK_M = 128;                      // queries per item == TMEM lanes
 constexpr int TILE_N = 64;                        // corpus rows per accumulator tile
-constexpr int STAGE_K = 128;                      // K elements per smem stage (two 64-wide TMA boxes)
+constexpr int MIN_STAGE_K = 128;                  // K elements per smem stage: 128 (2 TMA boxes) or 256 (4 boxes)
 constexpr int BOX_K = 64;                         // 64 bf16 = 128 bytes = one swizzle row
 constexpr int BOX_BYTES = TILE_N * BOX_K * 2;     // 8192
-constexpr int STAGE_BYTES = 2 * BOX_BYTES;        // 16384
+constexpr int MIN_STAGE_BYTES = 2 * BOX_BYTES;    // 16384
 constexpr int MAX_D = 768;
 constexpr int TMEM_COLS = 512;
 constexpr int ACC_COL0 = MAX_D / 2;               // accumulators live above the A operand
@@ -191,7 +191,12 @@ __device__ __forceinline__ uint64_t heap_replace_root(uint32_t lst, int kk, uint
   return lds_u64(lst);
 }
 
+// NBOX = 64-wide TMA boxes per ring stage.  A stage is the unit of the full/empty handshake: with 4 boxes
+// (K = 256 per stage) the MMA warp pays one barrier round trip per 16 MMAs instead of per 8.
+template <int NBOX>
 __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
+  constexpr int STAGE_K = NBOX * BOX_K;
+  constexpr int STAGE_BYTES = NBOX * BOX_BYTES;
   extern __shared__ uint8_t smem_dyn[];
   // carve: [ring | lists | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -252,8 +257,9 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
           if (elect_one()) {
             mbar_arrive_expect_tx(full + s, STAGE_BYTES);
             uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
-            tma_load_2d(&tmap, full + s, dst, ks * STAGE_K, t * TILE_N);
-            tma_load_2d(&tmap, full + s, dst + BOX_BYTES, ks * STAGE_K + BOX_K, t * TILE_N);
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b)
+              tma_load_2d(&tmap, full + s, dst + b * BOX_BYTES, ks * STAGE_K + b * BOX_K, t * TILE_N);
           }
           __syncwarp();
           if (++s == uint32_t(p.n_stages)) {
@@ -510,23 +516,26 @@ static EncodeTiledFn encode_tiled() {
 }
 
 struct Plan {
-  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups;
+  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups, nbox;
   size_t smem;
 };
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
-  if (dim % STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
+  if (dim % MIN_STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
+  pl.nbox = (dim % 256 == 0) ? 4 : 2;
+  const size_t STAGE_BYTES = size_t(pl.nbox) * BOX_BYTES;
+  const int MIN_ST = pl.nbox == 4 ? 3 : MIN_STAGES;
   if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
   // two candidate heaps per query (one per epilogue group) when they leave room for a >= 6-stage ring
   size_t fixed = 1024 /*align*/ + 2 * size_t(kk) * BLOCK_M * 8 + 6144 /*barriers, tmem slot, norm strips*/;
   pl.n_groups = 2;
-  if (fixed + 6 * size_t(STAGE_BYTES) > SMEM_LIMIT) {
+  if (fixed + 6 * size_t(MIN_STAGE_BYTES) > SMEM_LIMIT) {
     fixed -= size_t(kk) * BLOCK_M * 8;
     pl.n_groups = 1;
   }
-  if (fixed + size_t(MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
+  if (fixed + size_t(MIN_ST) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
-  if (ns > 12) ns = 12;
+  if (ns > 24 / pl.nbox) ns = 24 / pl.nbox;
   pl.n_stages = ns;
   pl.smem = fixed + size_t(ns) * STAGE_BYTES;
   pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
@@ -598,8 +607,13 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   const char* dbg = getenv("DRS_UMMA_DEBUG");
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
   DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
-  DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-  dense_umma_kernel<<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  if (pl.nbox == 4) {
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<4><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  } else {
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<2><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  }
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
