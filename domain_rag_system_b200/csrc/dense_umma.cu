@@ -522,9 +522,6 @@ struct Plan {
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
   if (dim % MIN_STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
-  pl.nbox = (dim % 256 == 0) ? 4 : 2;
-  const size_t STAGE_BYTES = size_t(pl.nbox) * BOX_BYTES;
-  const int MIN_ST = pl.nbox == 4 ? 3 : MIN_STAGES;
   if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
   // two candidate heaps per query (one per epilogue group) when they leave room for a >= 6-stage ring
   size_t fixed = 1024 /*align*/ + 2 * size_t(kk) * BLOCK_M * 8 + 6144 /*barriers, tmem slot, norm strips*/;
@@ -533,7 +530,10 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
     fixed -= size_t(kk) * BLOCK_M * 8;
     pl.n_groups = 1;
   }
-  if (fixed + size_t(MIN_ST) * STAGE_BYTES > SMEM_LIMIT) return false;
+  // 32 KB stages (K = 256) when the dimension allows and at least three of them fit; else 16 KB stages
+  pl.nbox = (dim % 256 == 0 && fixed + 3 * size_t(4 * BOX_BYTES) <= SMEM_LIMIT) ? 4 : 2;
+  const size_t STAGE_BYTES = size_t(pl.nbox) * BOX_BYTES;
+  if (fixed + size_t(pl.nbox == 4 ? 3 : MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
   if (ns > 24 / pl.nbox) ns = 24 / pl.nbox;
   pl.n_stages = ns;
