@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--ref-queries-per-step", type=int, default=4, help="--impl reference: queries per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-kernel", default="auto", choices=["auto", "simt", "umma"])
+    ap.add_argument("--rerank-top-n", type=int, default=0, help="simple cosine rerank pool (0 = no rerank); "
+                    "fetch_k = max(top_k, rerank_top_n) as in scripts/query.py:139")
+    ap.add_argument("--latency-calls", type=int, default=0, help="also time N sequential single-query calls (p50/p99)")
     return ap.parse_args()
 
 
@@ -207,7 +210,7 @@ def workload_config(args):
     return {"workload": f"BASELINE configs[1]: {args.chunks} chunks x {EMB_DIM}-d bf16, {args.queries}-query batch, "
                         f"top_k={args.top_k}, {args.fusion.upper()} fusion, BM25 Zipf(s=1.07) vocab {args.vocab}",
             "chunks": args.chunks, "queries_per_step": args.queries, "top_k": args.top_k, "kprime": 2 * args.top_k,
-            "fusion": args.fusion, "dim": EMB_DIM, "vocab": args.vocab,
+            "fusion": args.fusion, "rerank_top_n": args.rerank_top_n, "dim": EMB_DIM, "vocab": args.vocab,
             "l2": "inputs larger than L2 (bf16 corpus %.2f GB per pass)" % (args.chunks * EMB_DIM * 2 / 1e9),
             "parallelism": f"row-sharded x{args.gpus}" if args.gpus > 1 else "single GPU"}
 
@@ -255,14 +258,20 @@ def run_ours(args):
     q_terms_h, q_offs_h = ix.encode_queries(qt, pinned=True)
     qv_h = qv.contiguous().pin_memory()
     qv_d, q_terms_d, q_offs_d = qv_h.to(dev), q_terms_h.to(dev), q_offs_h.to(dev)
+    fetch_k = max(args.top_k, args.rerank_top_n) if args.rerank_top_n else args.top_k
+    assert not (args.rerank_top_n and world > 1), "rerank is measured on one GPU"
     ids_h = torch.empty(args.queries, args.top_k, dtype=torch.int64).pin_memory()
-    sc_h = torch.empty(args.queries, args.top_k, dtype=torch.float64).pin_memory()
+    sc_h = torch.empty(args.queries, args.top_k, dtype=torch.float32 if args.rerank_top_n else torch.float64).pin_memory()
     h2d = qv_h.numel() * 4 + q_terms_h.numel() * 4 + q_offs_h.numel() * 4
     d2h = ids_h.numel() * 8 + sc_h.numel() * 8
 
     def step_resident():
-        return searcher.search_batch(qv_d, q_terms_d, q_offs_d, top_k=args.top_k, fusion_method=args.fusion,
-                                     dense_kernel=kernel)
+        ids, sc = searcher.search_batch(qv_d, q_terms_d, q_offs_d, top_k=fetch_k, fusion_method=args.fusion,
+                                        dense_kernel=kernel)
+        if args.rerank_top_n:
+            pool = ids[:, : args.rerank_top_n].contiguous()
+            sc, ids, _ = _lib.rerank_cosine(emb, qv_d, pool, args.top_k)
+        return ids, sc
 
     def step_e2e():
         qv_d.copy_(qv_h, non_blocking=True)
@@ -334,6 +343,34 @@ def run_ours(args):
                      "sum_df_per_batch": sum_df, "ms_per_launch": b_ms / max(b_n, 1)}
     breakdown = {k: (v[0] / args.steps) for k, v in prof.items()}
 
+    # ---- latency mode: sequential single-query calls (BASELINE configs[4]) ---------------------------
+    latency = None
+    if args.latency_calls > 0 and world == 1:
+        nq = min(64, args.queries)
+        per_q = [ix.encode_queries([qt[i]]) for i in range(nq)]
+        per_q = [(a.to(dev), b.to(dev)) for a, b in per_q]
+        dev_ms, wall_ms = [], []
+        for c in range(args.latency_calls + 10):
+            i = c % nq
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t_w = time.perf_counter()
+            e0.record()
+            ids1, sc1 = searcher.search_batch(qv_d[i:i + 1], per_q[i][0], per_q[i][1], top_k=fetch_k,
+                                              fusion_method=args.fusion, dense_kernel=kernel)
+            if args.rerank_top_n:
+                sc1, ids1, _ = _lib.rerank_cosine(emb, qv_d[i:i + 1], ids1[:, : args.rerank_top_n].contiguous(), args.top_k)
+            e1.record()
+            torch.cuda.synchronize()
+            if c >= 10:
+                dev_ms.append(e0.elapsed_time(e1))
+                wall_ms.append(1e3 * (time.perf_counter() - t_w))
+        pct = lambda v, p: float(np.percentile(np.array(v), p))  # noqa: E731
+        latency = {"calls": args.latency_calls, "device_ms_p50": pct(dev_ms, 50), "device_ms_p99": pct(dev_ms, 99),
+                   "wall_ms_p50": pct(wall_ms, 50), "wall_ms_p99": pct(wall_ms, 99),
+                   "hbm_bytes_per_query_dense": 2.0 * n_local * EMB_DIM,
+                   "dense_hbm_floor_ms": 2.0 * n_local * EMB_DIM / (peaks["hbm_gbs"] * 1e9) * 1e3}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,7 +378,7 @@ def run_ours(args):
 
     # ---- CPU baseline + recall on a bounded sample (rank 0, single GPU only) ------------------------
     cpu_baseline, recall = None, None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.rerank_top_n:
         ids_gpu, sc_gpu = step_resident()
         ids_gpu, sc_gpu = ids_gpu.cpu().numpy(), sc_gpu.cpu().numpy()
         normed, bm = cpu_oracle_build(emb.float().cpu().numpy(), offs, toks, args.vocab)
@@ -366,6 +403,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "roofline": roofline, "roofline_bm25": roofline_bm25,
         "kernel_ms_per_step": breakdown, "cpu_baseline": cpu_baseline, "parity": recall, "clocks": clocks,
+        "latency": latency,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
