@@ -350,6 +350,7 @@ def run_ours(args):
         per_q = [ix.encode_queries([qt[i]]) for i in range(nq)]
         per_q = [(a.to(dev), b.to(dev)) for a, b in per_q]
         dev_ms, wall_ms = [], []
+        _lib.profile_enable(True)
         for c in range(args.latency_calls + 10):
             i = c % nq
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -365,10 +366,12 @@ def run_ours(args):
             if c >= 10:
                 dev_ms.append(e0.elapsed_time(e1))
                 wall_ms.append(1e3 * (time.perf_counter() - t_w))
+        lprof = {k: v[0] / max(v[1], 1) for k, v in _lib.profile_read().items()}   # ms per launch
+        _lib.profile_enable(False)
         pct = lambda v, p: float(np.percentile(np.array(v), p))  # noqa: E731
         latency = {"calls": args.latency_calls, "device_ms_p50": pct(dev_ms, 50), "device_ms_p99": pct(dev_ms, 99),
                    "wall_ms_p50": pct(wall_ms, 50), "wall_ms_p99": pct(wall_ms, 99),
-                   "hbm_bytes_per_query_dense": 2.0 * n_local * EMB_DIM,
+                   "kernel_ms_per_call": lprof, "hbm_bytes_per_query_dense": 2.0 * n_local * EMB_DIM,
                    "dense_hbm_floor_ms": 2.0 * n_local * EMB_DIM / (peaks["hbm_gbs"] * 1e9) * 1e3}
 
     if rank != 0:

@@ -74,7 +74,7 @@ static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim,
 }
 
 struct DenseWs {
-  size_t parts_keys, cand_keys, flags_off, gtau_off, total;
+  size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, total;
   int simt_parts, umma_parts, umma_qstride;
 };
 
@@ -89,7 +89,9 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   const size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk;
   w.parts_keys = std::max(simt_keys, umma_keys);
   w.cand_keys = size_t(n_queries) * kk;
-  w.flags_off = (w.parts_keys + w.cand_keys) * 8;
+  w.scratch_keys = std::max(merge_scratch_keys(w.simt_parts, n_queries, int(kk)),
+                            merge_scratch_keys(w.umma_parts, n_queries, int(kk)));
+  w.flags_off = (w.parts_keys + w.cand_keys + w.scratch_keys) * 8;
   w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
   w.total = w.gtau_off + size_t(w.umma_qstride) * 4 * (1 + size_t(w.umma_parts)) + 256;
   return w;
@@ -154,6 +156,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   cudaStream_t st = (cudaStream_t)stream;
   uint64_t* parts = reinterpret_cast<uint64_t*>(d_workspace);
   uint64_t* cand = parts + w.parts_keys;
+  uint64_t* scratch = w.scratch_keys ? cand + w.cand_keys : nullptr;
   int32_t* flags = d_out_flags ? d_out_flags
                                : reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.flags_off);
   g_last_dense_kernel = which;
@@ -166,7 +169,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
     }
     if (rc != DRS_OK) return rc;
     ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-    rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, nullptr, st);
+    rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, nullptr, scratch, st);
     if (rc != DRS_OK) return rc;
     return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk_s, kprime, 4e-6f,
                                 d_out_scores, d_out_ids, flags, nullptr, DRS_QMODE_EXACT, 1, 0, st);
@@ -179,7 +182,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   }
   if (rc != DRS_OK) return rc;
   ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-  rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, st);
+  rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, scratch, st);
   if (rc != DRS_OK) return rc;
   rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
                             d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st);
@@ -189,7 +192,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk_s, parts,
                          n_queries, flags, st);
   if (rc != DRS_OK) return rc;
-  rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, flags, st);
+  rc = launch_merge_keys(parts, w.simt_parts, n_queries, n_queries, kk_s, cand, flags, scratch, st);
   if (rc != DRS_OK) return rc;
   return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk_s, kprime, 4e-6f,
                               d_out_scores, d_out_ids, flags, flags, DRS_QMODE_EXACT, 3, 2, st);

@@ -381,6 +381,7 @@ static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& gy,
   const int q = n_queries > 0 ? n_queries : 1;
   gx = (8 * target + q - 1) / q;
   if (gx > ix->n_tiles) gx = ix->n_tiles;
+  if (gx > target) gx = target;   // never more slices than resident CTAs: each slice hands in a list to merge
   if (gx < 1) gx = 1;
   tiles_per_cta = (ix->n_tiles + gx - 1) / gx;
   if (tiles_per_cta < 1) tiles_per_cta = 1;
@@ -404,6 +405,7 @@ extern "C" size_t drs_bm25_workspace_bytes(int n_queries, const drs_bm25_index* 
   size_t b = size_t(gx) * n_queries * kk * 8;  // partial lists
   b += size_t(n_queries) * kk * 8;             // merged candidates
   b += size_t(n_queries) * 8;                  // shared thresholds
+  b += merge_scratch_keys(gx, n_queries, int(kk)) * 8;  // two-level merge scratch
   return b + 256;
 }
 
@@ -439,7 +441,8 @@ extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_ter
   }
   DRS_CUDA_CHECK(cudaGetLastError());
   ProfScope pt(DRS_PROF_BM25_TAIL, st);
-  int rc = launch_merge_keys(parts, gx, n_queries, n_queries, kk, cand, nullptr, st);
+  uint64_t* mscratch = merge_scratch_keys(gx, n_queries, kk) ? reinterpret_cast<uint64_t*>(gtau + n_queries) : nullptr;
+  int rc = launch_merge_keys(parts, gx, n_queries, n_queries, kk, cand, nullptr, mscratch, st);
   if (rc != DRS_OK) return rc;
   bm25_rescore_kernel<<<n_queries, 256, 0, st>>>(ix, d_q_terms, d_q_offsets, cand, kk, kprime, d_out_scores,
                                                  d_out_ids);

@@ -7,19 +7,26 @@
 namespace drs {
 
 // ------------------------------------------------------------------------------------------
-// merge_keys: one CTA per query.  Input: n_parts lists of kk u64 keys each (unsorted, 0 =
-// empty), laid out parts[(p * q_stride + q) * kk + c].  Output: the kk largest keys,
-// descending.  Chunked block bitonic sort so any n_parts works.
+// merge_keys: CTA (q, g) merges parts [g*ppc, (g+1)*ppc) of query q.  Input: lists of kk u64 keys
+// (unsorted, 0 = empty) laid out parts[(p * q_stride + q) * kk + c].  Output: the kk largest keys,
+// descending, at out[(g * out_qstride + q) * kk ..].  Chunked block bitonic sort.  With many parts
+// (single-query latency mode: hundreds of CTAs each hand in a list) the merge runs in two levels
+// so that it is spread over many CTAs instead of one.
 // ------------------------------------------------------------------------------------------
 constexpr int MERGE_BUF = 2048;
+constexpr int MERGE_FANIN = 16;       // parts per CTA in the first level of a two-level merge
+constexpr int MERGE_TWO_LEVEL = 48;   // more parts than this => two levels
 
 __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restrict__ parts, int n_parts,
                                                          int q_stride, int kk, uint64_t* __restrict__ out,
-                                                         const int32_t* __restrict__ active) {
+                                                         int out_qstride, const int32_t* __restrict__ active,
+                                                         int ppc) {
   __shared__ uint64_t buf[MERGE_BUF];
   const int q = blockIdx.x;
   if (active != nullptr && active[q] == 0) return;
-  const int n = n_parts * kk;
+  const int p0 = blockIdx.y * ppc;
+  const int np = min(ppc, n_parts - p0);
+  const int n = np * kk;
   for (int i = threadIdx.x; i < kk; i += blockDim.x) buf[i] = 0;
   int pos = 0;
   while (pos < n) {
@@ -30,7 +37,7 @@ __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restr
       if (i < take) {
         const int f = pos + i;
         const int p = f / kk, c = f - p * kk;
-        v = parts[(size_t(p) * q_stride + q) * kk + c];
+        v = parts[(size_t(p0 + p) * q_stride + q) * kk + c];
       }
       buf[kk + i] = v;
     }
@@ -39,14 +46,31 @@ __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restr
     pos += take;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kk; i += blockDim.x) out[size_t(q) * kk + i] = buf[i];
+  for (int i = threadIdx.x; i < kk; i += blockDim.x)
+    out[(size_t(blockIdx.y) * out_qstride + q) * kk + i] = buf[i];
+}
+
+size_t merge_scratch_keys(int n_parts, int n_queries, int kk) {
+  if (n_parts <= MERGE_TWO_LEVEL) return 0;
+  return size_t((n_parts + MERGE_FANIN - 1) / MERGE_FANIN) * n_queries * kk;
 }
 
 int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
-                      uint64_t* d_out, const int32_t* d_active, cudaStream_t st) {
+                      uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, cudaStream_t st) {
   DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2, DRS_ERR_UNSUPPORTED, "merge: list length out of range");
-  merge_keys_kernel<<<n_queries, 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_out, d_active);
-  count_launches(1);
+  if (n_parts > MERGE_TWO_LEVEL && d_scratch != nullptr) {
+    const int g1 = (n_parts + MERGE_FANIN - 1) / MERGE_FANIN;
+    merge_keys_kernel<<<dim3(n_queries, g1), 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_scratch, n_queries,
+                                                            d_active, MERGE_FANIN);
+    count_launches(1);
+    merge_keys_kernel<<<dim3(n_queries, 1), 256, 0, st>>>(d_scratch, g1, n_queries, kk, d_out, n_queries, d_active,
+                                                           g1);
+    count_launches(1);
+  } else {
+    merge_keys_kernel<<<dim3(n_queries, 1), 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_out, n_queries, d_active,
+                                                           n_parts);
+    count_launches(1);
+  }
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
 }
