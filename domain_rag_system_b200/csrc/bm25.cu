@@ -260,18 +260,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         __syncthreads();
       }
       // ---- scan the tile, highest document first -----------------------------------------
-      // While this CTA has no threshold yet for the query (cold list, nothing published by other CTAs)
-      // only 256 documents are scanned before the first merge, so the first sort is small.
-      int done = 0;
-      while (done < T) {
+      // Four consecutive documents per thread: one 16-byte shared load and a max test reject almost every
+      // group once the threshold is warm.  While this CTA has no threshold yet for the query (cold list,
+      // nothing published by other CTAs) only BM25_COLD_STEP documents are scanned before the first
+      // merge, so the first sort is small; a warm CTA sweeps the rest of the tile in one go.
+      auto scan_range = [&](int from, int count) {   // documents T-1-from downwards
         const unsigned long long tau = s_tau;
-        const bool cold = (tau == 0);
-        const float tau_s = cold ? -INFINITY : key_score(tau);
-        const int step = cold ? BM25_COLD_STEP : BM25_SEG;
-        // four consecutive documents per thread: one 16-byte shared load and a max test reject almost
-        // every group once the threshold is warm
-        if (4 * tid < step && done + 4 * tid < T) {
-          const int hi = T - 1 - done - 4 * tid;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
+        const float tau_s = tau == 0 ? -INFINITY : key_score(tau);
+        for (int g = 4 * tid; g < count && from + g < T; g += 4 * BM25_THREADS) {
+          const int hi = T - 1 - from - g;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
           const float4 v = *reinterpret_cast<const float4*>(sc + hi - 3);
           if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tau_s) {
             const float vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
@@ -288,14 +285,34 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             }
           }
         }
-        done += step;
+      };
+      int done = 0;
+      while (done < T) {
+        const bool cold = (s_tau == 0);
+        const int step = cold ? BM25_COLD_STEP : T - done;
+        const int cnt_before = s_cnt;
         __syncthreads();
-        // Merge (sort list + survivors, tighten the threshold) when the append area could overflow in
-        // the next segment, when enough survivors piled up that a tighter threshold pays for the
-        // sort, as soon as a cold list can be filled, and at the very end of this CTA's tiles.
+        scan_range(done, step);
+        __syncthreads();
+        if (s_cnt > cap) {
+          // more survivors than the append area holds (some were dropped): redo the range in segments
+          // that cannot overflow, merging whenever the area fills up
+          __syncthreads();
+          if (tid == 0) s_cnt = cnt_before;
+          __syncthreads();
+          for (int d2 = done; d2 < done + step; d2 += BM25_SEG) {
+            if (s_cnt > cap - BM25_SEG) merge(q);
+            scan_range(d2, min(BM25_SEG, done + step - d2));
+            __syncthreads();
+          }
+        }
+        done += step;
+        // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a
+        // tighter threshold pays for the sort, as soon as a cold list can be filled, when the append
+        // area is half full, and at the very end of this CTA's tiles.
         const bool last = (done >= T) && (j == tile_lo);
         const int cnt = s_cnt;
-        if (cnt > 0 && (last || cnt > cap - BM25_SEG || cnt >= BM25_MERGE_AT || (cold && cnt >= kk))) merge(q);
+        if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || (cold && cnt >= kk))) merge(q);
       }
     }
     for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];

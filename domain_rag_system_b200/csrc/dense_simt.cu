@@ -164,8 +164,22 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
     }
   };
 
-  // two rows in flight per warp
+  // rows in flight per warp: four when the queries leave registers for it (latency mode: the kernel is
+  // purely HBM-bound and needs ~64 KB of loads outstanding per SM), else two
   int64_t r = r_begin + warp;
+  if (QT <= 2) {
+    for (; r + 3 * SIMT_WARPS < r_end; r += 4 * SIMT_WARPS) {
+      uint4 w0[NCH], w1[NCH], w2[NCH], w3[NCH];
+      load_row(r, w0);
+      load_row(r + SIMT_WARPS, w1);
+      load_row(r + 2 * SIMT_WARPS, w2);
+      load_row(r + 3 * SIMT_WARPS, w3);
+      score_row(r, w0);
+      score_row(r + SIMT_WARPS, w1);
+      score_row(r + 2 * SIMT_WARPS, w2);
+      score_row(r + 3 * SIMT_WARPS, w3);
+    }
+  }
   for (; r + SIMT_WARPS < r_end; r += 2 * SIMT_WARPS) {
     uint4 w0[NCH], w1[NCH];
     load_row(r, w0);

@@ -407,3 +407,19 @@ def test_multi_gpu_sharded_search_matches_single_gpu():
            "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "dist_gpu_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "DIST_CHECK_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_bm25_adversarial_monotone_scores_overflow_path():
+    """Scores that keep increasing in scan order (every document beats the running k'-th best) overflow the
+    survivor area of a warm tile sweep; the kernel must fall back to segment-wise merging, and the groups of
+    four exactly tied documents must come out larger-id first."""
+    n, length = 12288, 3200
+    tf = 1 + (n - 1 - np.arange(n)) // 4
+    offs = np.arange(n + 1, dtype=np.int64) * length
+    toks = np.ones(n * length, dtype=np.int32)
+    for i in range(n):
+        toks[offs[i]:offs[i] + tf[i]] = 0
+    toks[offs[n - 1] + length - 1] = 2          # a third term so that idf values differ
+    queries = [np.array([0], dtype=np.int32), np.array([0, 1, 0], dtype=np.int32), np.array([1], dtype=np.int32)]
+    _check_bm25(offs, toks, 3, queries, 20, tile_docs=8192, dense_frac=0.0)
+    _check_bm25(offs, toks, 3, queries, 20, tile_docs=8192)
