@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
     const bool one_chunk = (t1 - t0) <= BM25_TCHUNK;
+    long long seen = 0;   // documents scanned so far for this (slice, query)
     if (one_chunk) stage_terms(t0, t1 - t0);
     for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
     if (tid == 0) {
@@ -289,7 +290,12 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       int done = 0;
       while (done < T) {
         const bool cold = (s_tau == 0);
-        const int step = cold ? BM25_COLD_STEP : T - done;
+        // Steps grow geometrically with the number of documents this (slice, query) has seen: a step of 3x the
+        // documents seen yields about 3*kk survivors, so every early merge is a small sort.
+        const long long grow = 3 * seen;
+        long long want = grow > BM25_COLD_STEP ? grow : BM25_COLD_STEP;
+        if (want > T - done) want = T - done;
+        const int step = cold ? BM25_COLD_STEP : int(want);
         const int cnt_before = s_cnt;
         __syncthreads();
         scan_range(done, step);
@@ -307,12 +313,14 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           }
         }
         done += step;
+        seen += step;
         // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a
         // tighter threshold pays for the sort, as soon as a cold list can be filled, when the append
         // area is half full, and at the very end of this CTA's tiles.
         const bool last = (done >= T) && (j == tile_lo);
         const int cnt = s_cnt;
-        if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || (cold && cnt >= kk))) merge(q);
+        if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk)))
+          merge(q);
       }
     }
     for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];
