@@ -29,6 +29,29 @@ class _NoAbbreviations:
     abbreviations: Dict[str, str] = {}
 
 
+class _PickledObject:
+    """Attribute bag standing in for a class whose module is not installed here (e.g. the
+    ``rank_bm25.BM25Okapi`` object inside a ``bm25_index.pkl`` written by the reference,
+    ``src/indexing/bm25_indexer.py:165-181``).  Nothing is computed with it: the device index is rebuilt
+    from the ``tokenized_corpus`` the same pickle carries."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+
+def _load_pickle_with_shims(f):
+    """``pickle.load`` that tolerates classes from modules missing in this environment."""
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            try:
+                return super().find_class(module, name)
+            except (ImportError, AttributeError):
+                if module.split(".")[0] in ("rank_bm25",):
+                    return type(name, (_PickledObject,), {"__module__": module})
+                raise
+    return _Unpickler(f).load()
+
+
 def chunk_as_dict(chunk) -> Dict:
     return chunk.to_dict() if hasattr(chunk, "to_dict") else chunk
 
@@ -117,7 +140,7 @@ class BM25Indexer:
         if not filepath.exists():
             raise FileNotFoundError(f"Index file not found: {filepath}")
         with open(filepath, "rb") as f:
-            data = pickle.load(f)
+            data = _load_pickle_with_shims(f)
         self.chunks = data["chunks"]
         self.tokenized_corpus = data["tokenized_corpus"]
         self.k1, self.b = data["k1"], data["b"]

@@ -117,3 +117,41 @@ def test_dense_head_term_rows_match_postings():
         assert np.array_equal(dense[slot[t]], row)
     off = Bm25DeviceIndex.from_token_ids(offs, toks, 60, device="cpu", tile_docs=256, dense_frac=0.0)
     assert off.n_dense == 0
+
+
+def test_load_reference_style_bm25_pickle_without_rank_bm25(tmp_path):
+    """A bm25_index.pkl as the reference writes it (bm25_indexer.py:165-181) holds a rank_bm25.BM25Okapi
+    object; rank_bm25 is not installed here.  load() must still work and rebuild the device index from the
+    tokenised corpus in the pickle (statistics identical to the pickled object's)."""
+    import pickle
+    import sys
+    import types
+    from domain_rag_system_b200.indexing.bm25_indexer import BM25Indexer
+    docs = [["aspirin", "pain", "relief"], ["aspirin", "side", "effects", "bleeding"], ["ibuprofen", "pain"]]
+    chunks = [{"chunk_id": f"c{i}", "text": " ".join(d)} for i, d in enumerate(docs)]
+    mod = types.ModuleType("rank_bm25")               # a throw-away rank_bm25 with the oracle's restatement
+
+    class BM25Okapi(obm25.BM25OkapiRestated):
+        pass
+    BM25Okapi.__module__ = "rank_bm25"
+    BM25Okapi.__qualname__ = "BM25Okapi"
+    mod.BM25Okapi = BM25Okapi
+    sys.modules["rank_bm25"] = mod
+    try:
+        ref_obj = BM25Okapi(docs, k1=1.2, b=0.6)
+        with open(tmp_path / "bm25_index.pkl", "wb") as f:
+            pickle.dump({"bm25": ref_obj, "chunks": chunks, "tokenized_corpus": docs, "k1": 1.2, "b": 0.6}, f)
+    finally:
+        del sys.modules["rank_bm25"]
+    bi = BM25Indexer(k1=1.5, b=0.75, device="cpu")
+    bi.load(str(tmp_path / "bm25_index.pkl"))
+    assert (bi.k1, bi.b) == (1.2, 0.6) and bi.chunks == chunks and bi.tokenized_corpus == docs
+    assert bi.bm25.avgdl == ref_obj.avgdl and bi.bm25.average_idf == ref_obj.average_idf
+    for w, i in bi.bm25.vocab.items():
+        assert bi.bm25.t["idf"][i].item() == ref_obj.idf[w]
+    assert bi.get_stats() == {"num_documents": 3, "avg_doc_length": 3.0, "vocab_size": 7, "k1": 1.2, "b": 0.6}
+    # round trip through our own format
+    bi.save(str(tmp_path / "ours.pkl"))
+    bj = BM25Indexer(device="cpu")
+    bj.load(str(tmp_path / "ours.pkl"))
+    assert bj.bm25.avgdl == bi.bm25.avgdl and torch.equal(bj.bm25.t["post_doc"], bi.bm25.t["post_doc"])
