@@ -1,15 +1,28 @@
-// BM25 over a term-major CSR inverted index, document-partitioned into tiles.
+// BM25 over a term-major CSR inverted index, document-partitioned into tiles of 8192 documents.
 //
-// Stage 1 (bm25_select): HBM-bound.  A CTA owns a run of document tiles.  For one query and one
-// tile it zeroes a shared-memory fp32 score tile, then walks the query's term occurrences IN
-// ORDER; for each it streams the slice of that term's postings that falls inside the tile
-// (coalesced doc-id + impact reads, 8 bytes per posting) and adds the precomputed fp32 impact
-// into the tile.  One barrier per term: inside a term every document appears once, so the adds
-// need no atomics and every document's fp32 sum is formed in the same order => documents that
-// tie exactly in the reference's fp64 arithmetic tie exactly here too.  The tile is then
-// scanned against a running threshold and survivors are merged into the CTA's top-kk list.
-// Tiles and documents are visited in DESCENDING order so that, among equal scores, the larger
-// document id (which the tie rule prefers) is seen first and later equal scores are rejected.
+// Stage 1 (bm25_select).  A CTA owns a run of consecutive tiles (an x-slice) and walks ALL of them for one
+// query before taking its next query (grid.y strides over the queries), so its threshold is warm after the
+// first tile.  Per (tile, query):
+//   * pass A -- the query's head terms (df >= N/4, ~80 % of a Zipfian query's postings) are added from
+//     DENSE per-document impact rows, up to four rows fused per sweep (16-byte loads, no scatter); the
+//     first sweep also initialises the shared-memory fp32 score tile;
+//   * pass B -- every other term streams the slice of its postings inside the tile (16-byte loads of doc
+//     ids and fp32 impacts, 8 bytes per posting), one term per barrier: a term never repeats a document,
+//     so its read-modify-writes need no atomics, and the next term's first loads are issued before the
+//     barrier;
+//   * scan -- highest document first, four documents per 16-byte shared load, against a 64-bit
+//     (score, doc) threshold; survivors go to an append area and are merged into the CTA's top-kk by a
+//     block bitonic sort when enough pile up.  Scan steps grow geometrically while the list is young so
+//     the early sorts stay small; a global per-query threshold (atomicMax) lets CTAs prune each other.
+// Term metadata is staged once per (CTA, query).
+// Additions into a document's score always happen in the same order (head terms in query order, then
+// the other terms in query order), so documents with identical (term, impact) patterns get identical
+// fp32 sums: the reference's exact fp64 ties survive this fp32 pre-selection.  Tiles and documents are
+// visited in DESCENDING order so that, among equal scores, the larger document id (which the tie rule
+// prefers) is seen first and later equal scores are rejected.
+// The kernel's algorithmic traffic is 8 bytes per posting visited; measured DRAM traffic is ~10x lower
+// (queries share head-term rows through L2), so its practical bound is shared-memory read-modify-writes
+// and the ~7 us of barriers and dependent loads every (tile, query) pair pays.
 //
 // Stage 2 (bm25_rescore): the kk surviving candidates per query are re-scored in fp64 with
 // rank_bm25's exact operation order (tf looked up by binary search), sorted by

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
     const float* __restrict__ queries, int n_queries, int q0, const __nv_bfloat16* __restrict__ corpus,
     const float* __restrict__ inv_norm, const uint8_t* __restrict__ mask, int64_t n_rows, int dim,
     int64_t rows_per_cta, int kk, uint64_t* __restrict__ parts, int q_stride,
-    const int32_t* __restrict__ active, int pass) {
+    const int32_t* __restrict__ active, int n_passes) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* lists = reinterpret_cast<uint64_t*>(smem_raw);              // [WARPS][QT][kk]
   uint64_t* sortbuf = lists + SIMT_WARPS * QT * kk;                     // [SIMT_SORT_BUF]
@@ -55,164 +55,169 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  // which queries does this pass serve?
-  if (threadIdx.x < 32) {
-    if (active == nullptr) {
-      if (lane < QT) qidx[lane] = (q0 + lane < n_queries) ? q0 + lane : -1;
-    } else {
-      // the (pass*QT + j)-th active query, j < QT
-      if (lane < QT) qidx[lane] = -1;
-      __syncwarp();
-      int seen = 0;
-      const int want0 = pass * QT;
-      for (int base = 0; base < n_queries && seen < want0 + QT; base += 32) {
-        const int q = base + lane;
-        const bool a = (q < n_queries) && (active[q] != 0);
-        const unsigned b = __ballot_sync(0xffffffffu, a);
-        if (a) {
-          const int ord = seen + __popc(b & ((1u << lane) - 1u));
-          if (ord >= want0 && ord < want0 + QT) qidx[ord - want0] = q;
-        }
-        seen += __popc(b);
-      }
-    }
-  }
-  __syncthreads();
-  bool any = false;
-#pragma unroll
-  for (int j = 0; j < QT; ++j) any |= (qidx[j] >= 0);
-  if (!any) return;
-
-  // queries -> registers (element order of the lane)
-  float qr[QT][NCH * 8];
-#pragma unroll
-  for (int j = 0; j < QT; ++j) {
-    const int q = qidx[j];
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int e = ch * 256 + lane * 8;
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        qr[j][ch * 8 + t] = (q >= 0 && e + t < dim) ? queries[size_t(q) * dim + e + t] : 0.0f;
-    }
-  }
-  uint64_t* mylist = lists + size_t(warp) * QT * kk;
-  for (int i = lane; i < QT * kk; i += 32) mylist[i] = 0;
-  __syncwarp();
-  float tau[QT];
-  uint64_t tau_key[QT];
-#pragma unroll
-  for (int j = 0; j < QT; ++j) {
-    tau[j] = -INFINITY;
-    tau_key[j] = 0;
-  }
-
-  const int64_t r_begin = int64_t(blockIdx.x) * rows_per_cta;
-  const int64_t r_end = min(n_rows, r_begin + rows_per_cta);
-
-  auto load_row = [&](int64_t r, uint4 (&w)[NCH]) {
-    const uint4* rp = reinterpret_cast<const uint4*>(corpus + size_t(r) * dim);
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const int e = ch * 256 + lane * 8;
-      w[ch] = (e < dim) ? __ldg(rp + (e >> 3)) : make_uint4(0, 0, 0, 0);
-    }
-  };
-  auto score_row = [&](int64_t r, const uint4 (&w)[NCH]) {
-    if (mask != nullptr && mask[r] == 0) return;
-    float acc[QT];
-#pragma unroll
-    for (int j = 0; j < QT; ++j) acc[j] = 0.0f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-      const float c0 = bf16_lo(w[ch].x), c1 = bf16_hi(w[ch].x), c2 = bf16_lo(w[ch].y), c3 = bf16_hi(w[ch].y);
-      const float c4 = bf16_lo(w[ch].z), c5 = bf16_hi(w[ch].z), c6 = bf16_lo(w[ch].w), c7 = bf16_hi(w[ch].w);
-#pragma unroll
-      for (int j = 0; j < QT; ++j) {
-        const float* qq = &qr[j][ch * 8];
-        acc[j] = fmaf(c0, qq[0], acc[j]);
-        acc[j] = fmaf(c1, qq[1], acc[j]);
-        acc[j] = fmaf(c2, qq[2], acc[j]);
-        acc[j] = fmaf(c3, qq[3], acc[j]);
-        acc[j] = fmaf(c4, qq[4], acc[j]);
-        acc[j] = fmaf(c5, qq[5], acc[j]);
-        acc[j] = fmaf(c6, qq[6], acc[j]);
-        acc[j] = fmaf(c7, qq[7], acc[j]);
-      }
-    }
-    const float nrm = __ldg(inv_norm + r);
-#pragma unroll
-    for (int j = 0; j < QT; ++j) {
-      float a = acc[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      const float s = a * nrm;
-      if (s >= tau[j] && qidx[j] >= 0) {  // warp-uniform
-        const uint64_t key = make_key(s, uint32_t(r));
-        if (key > tau_key[j]) {
-          uint64_t* lst = mylist + j * kk;
-          uint64_t mk;
-          int mp;
-          warp_argmin(lst, kk, lane, mk, mp);
-          if (lane == 0) lst[mp] = key;
-          __syncwarp();
-          warp_argmin(lst, kk, lane, mk, mp);
-          tau_key[j] = mk;
-          tau[j] = mk ? key_score(mk) : -INFINITY;
+  // active != nullptr: up to n_passes passes over the corpus, QT flagged queries each (the escalation of
+  // queries whose tensor-core result is unproven); the loop ends at the first pass with nothing to do.
+  for (int pass = 0; pass < n_passes; ++pass) {
+    // which queries does this pass serve?
+    if (threadIdx.x < 32) {
+      if (active == nullptr) {
+        if (lane < QT) qidx[lane] = (q0 + lane < n_queries) ? q0 + lane : -1;
+      } else {
+        // the (pass*QT + j)-th active query, j < QT
+        if (lane < QT) qidx[lane] = -1;
+        __syncwarp();
+        int seen = 0;
+        const int want0 = pass * QT;
+        for (int base = 0; base < n_queries && seen < want0 + QT; base += 32) {
+          const int q = base + lane;
+          const bool a = (q < n_queries) && (active[q] != 0);
+          const unsigned b = __ballot_sync(0xffffffffu, a);
+          if (a) {
+            const int ord = seen + __popc(b & ((1u << lane) - 1u));
+            if (ord >= want0 && ord < want0 + QT) qidx[ord - want0] = q;
+          }
+          seen += __popc(b);
         }
       }
-    }
-  };
-
-  // rows in flight per warp: four when the queries leave registers for it (latency mode: the kernel is
-  // purely HBM-bound and needs ~64 KB of loads outstanding per SM), else two
-  int64_t r = r_begin + warp;
-  if (QT <= 2) {
-    for (; r + 3 * SIMT_WARPS < r_end; r += 4 * SIMT_WARPS) {
-      uint4 w0[NCH], w1[NCH], w2[NCH], w3[NCH];
-      load_row(r, w0);
-      load_row(r + SIMT_WARPS, w1);
-      load_row(r + 2 * SIMT_WARPS, w2);
-      load_row(r + 3 * SIMT_WARPS, w3);
-      score_row(r, w0);
-      score_row(r + SIMT_WARPS, w1);
-      score_row(r + 2 * SIMT_WARPS, w2);
-      score_row(r + 3 * SIMT_WARPS, w3);
-    }
-  }
-  for (; r + SIMT_WARPS < r_end; r += 2 * SIMT_WARPS) {
-    uint4 w0[NCH], w1[NCH];
-    load_row(r, w0);
-    load_row(r + SIMT_WARPS, w1);
-    score_row(r, w0);
-    score_row(r + SIMT_WARPS, w1);
-  }
-  if (r < r_end) {
-    uint4 w0[NCH];
-    load_row(r, w0);
-    score_row(r, w0);
-  }
-  __syncthreads();
-
-  // per-CTA merge of the warps' lists, one query at a time
-  const int n = SIMT_WARPS * kk;
-  const int m = next_pow2(n);
-#pragma unroll 1
-  for (int j = 0; j < QT; ++j) {
-    const int q = qidx[j];
-    if (q < 0) continue;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
-      uint64_t v = 0;
-      if (i < n) {
-        const int w = i / kk, c = i - w * kk;
-        v = lists[(size_t(w) * QT + j) * kk + c];
-      }
-      sortbuf[i] = v;
     }
     __syncthreads();
-    block_bitonic_desc(sortbuf, m, [](uint64_t a, uint64_t b) { return a < b; });
-    for (int i = threadIdx.x; i < kk; i += blockDim.x)
-      parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = sortbuf[i];
+    bool any = false;
+  #pragma unroll
+    for (int j = 0; j < QT; ++j) any |= (qidx[j] >= 0);
+    if (!any) break;   // no (more) flagged queries
+
+    // queries -> registers (element order of the lane)
+    float qr[QT][NCH * 8];
+  #pragma unroll
+    for (int j = 0; j < QT; ++j) {
+      const int q = qidx[j];
+  #pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int e = ch * 256 + lane * 8;
+  #pragma unroll
+        for (int t = 0; t < 8; ++t)
+          qr[j][ch * 8 + t] = (q >= 0 && e + t < dim) ? queries[size_t(q) * dim + e + t] : 0.0f;
+      }
+    }
+    uint64_t* mylist = lists + size_t(warp) * QT * kk;
+    for (int i = lane; i < QT * kk; i += 32) mylist[i] = 0;
+    __syncwarp();
+    float tau[QT];
+    uint64_t tau_key[QT];
+  #pragma unroll
+    for (int j = 0; j < QT; ++j) {
+      tau[j] = -INFINITY;
+      tau_key[j] = 0;
+    }
+
+    const int64_t r_begin = int64_t(blockIdx.x) * rows_per_cta;
+    const int64_t r_end = min(n_rows, r_begin + rows_per_cta);
+
+    auto load_row = [&](int64_t r, uint4 (&w)[NCH]) {
+      const uint4* rp = reinterpret_cast<const uint4*>(corpus + size_t(r) * dim);
+  #pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const int e = ch * 256 + lane * 8;
+        w[ch] = (e < dim) ? __ldg(rp + (e >> 3)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto score_row = [&](int64_t r, const uint4 (&w)[NCH]) {
+      if (mask != nullptr && mask[r] == 0) return;
+      float acc[QT];
+  #pragma unroll
+      for (int j = 0; j < QT; ++j) acc[j] = 0.0f;
+  #pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        const float c0 = bf16_lo(w[ch].x), c1 = bf16_hi(w[ch].x), c2 = bf16_lo(w[ch].y), c3 = bf16_hi(w[ch].y);
+        const float c4 = bf16_lo(w[ch].z), c5 = bf16_hi(w[ch].z), c6 = bf16_lo(w[ch].w), c7 = bf16_hi(w[ch].w);
+  #pragma unroll
+        for (int j = 0; j < QT; ++j) {
+          const float* qq = &qr[j][ch * 8];
+          acc[j] = fmaf(c0, qq[0], acc[j]);
+          acc[j] = fmaf(c1, qq[1], acc[j]);
+          acc[j] = fmaf(c2, qq[2], acc[j]);
+          acc[j] = fmaf(c3, qq[3], acc[j]);
+          acc[j] = fmaf(c4, qq[4], acc[j]);
+          acc[j] = fmaf(c5, qq[5], acc[j]);
+          acc[j] = fmaf(c6, qq[6], acc[j]);
+          acc[j] = fmaf(c7, qq[7], acc[j]);
+        }
+      }
+      const float nrm = __ldg(inv_norm + r);
+  #pragma unroll
+      for (int j = 0; j < QT; ++j) {
+        float a = acc[j];
+  #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        const float s = a * nrm;
+        if (s >= tau[j] && qidx[j] >= 0) {  // warp-uniform
+          const uint64_t key = make_key(s, uint32_t(r));
+          if (key > tau_key[j]) {
+            uint64_t* lst = mylist + j * kk;
+            uint64_t mk;
+            int mp;
+            warp_argmin(lst, kk, lane, mk, mp);
+            if (lane == 0) lst[mp] = key;
+            __syncwarp();
+            warp_argmin(lst, kk, lane, mk, mp);
+            tau_key[j] = mk;
+            tau[j] = mk ? key_score(mk) : -INFINITY;
+          }
+        }
+      }
+    };
+
+    // rows in flight per warp: four when the queries leave registers for it (latency mode: the kernel is
+    // purely HBM-bound and needs ~64 KB of loads outstanding per SM), else two
+    int64_t r = r_begin + warp;
+    if (QT <= 2) {
+      for (; r + 3 * SIMT_WARPS < r_end; r += 4 * SIMT_WARPS) {
+        uint4 w0[NCH], w1[NCH], w2[NCH], w3[NCH];
+        load_row(r, w0);
+        load_row(r + SIMT_WARPS, w1);
+        load_row(r + 2 * SIMT_WARPS, w2);
+        load_row(r + 3 * SIMT_WARPS, w3);
+        score_row(r, w0);
+        score_row(r + SIMT_WARPS, w1);
+        score_row(r + 2 * SIMT_WARPS, w2);
+        score_row(r + 3 * SIMT_WARPS, w3);
+      }
+    }
+    for (; r + SIMT_WARPS < r_end; r += 2 * SIMT_WARPS) {
+      uint4 w0[NCH], w1[NCH];
+      load_row(r, w0);
+      load_row(r + SIMT_WARPS, w1);
+      score_row(r, w0);
+      score_row(r + SIMT_WARPS, w1);
+    }
+    if (r < r_end) {
+      uint4 w0[NCH];
+      load_row(r, w0);
+      score_row(r, w0);
+    }
+    __syncthreads();
+
+    // per-CTA merge of the warps' lists, one query at a time
+    const int n = SIMT_WARPS * kk;
+    const int m = next_pow2(n);
+  #pragma unroll 1
+    for (int j = 0; j < QT; ++j) {
+      const int q = qidx[j];
+      if (q < 0) continue;
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        uint64_t v = 0;
+        if (i < n) {
+          const int w = i / kk, c = i - w * kk;
+          v = lists[(size_t(w) * QT + j) * kk + c];
+        }
+        sortbuf[i] = v;
+      }
+      __syncthreads();
+      block_bitonic_desc(sortbuf, m, [](uint64_t a, uint64_t b) { return a < b; });
+      for (int i = threadIdx.x; i < kk; i += blockDim.x)
+        parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = sortbuf[i];
+      __syncthreads();
+    }
     __syncthreads();
   }
 }
@@ -256,7 +261,7 @@ int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, con
     for (int q0 = 0; q0 < n_queries;) {
       const int left = n_queries - q0;
       const int qt = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
-      const int pass = 0;
+      const int pass = 1;
       int rc = DRS_ERR_UNSUPPORTED;
       DRS_SIMT_CASE(1, 1) DRS_SIMT_CASE(1, 2) DRS_SIMT_CASE(1, 3) DRS_SIMT_CASE(1, 4)
       DRS_SIMT_CASE(2, 1) DRS_SIMT_CASE(2, 2) DRS_SIMT_CASE(2, 3) DRS_SIMT_CASE(2, 4)
@@ -265,12 +270,10 @@ int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, con
       q0 += qt;
     }
   } else {
-    for (int pass = 0; pass < 4; ++pass) {
-      const int qt = 4, q0 = 0;
-      int rc = DRS_ERR_UNSUPPORTED;
-      DRS_SIMT_CASE(4, 1) DRS_SIMT_CASE(4, 2) DRS_SIMT_CASE(4, 3) DRS_SIMT_CASE(4, 4)
-      if (rc != DRS_OK) return rc;
-    }
+    const int qt = 4, q0 = 0, pass = 4;   // one launch, up to four passes inside the kernel
+    int rc = DRS_ERR_UNSUPPORTED;
+    DRS_SIMT_CASE(4, 1) DRS_SIMT_CASE(4, 2) DRS_SIMT_CASE(4, 3) DRS_SIMT_CASE(4, 4)
+    if (rc != DRS_OK) return rc;
   }
 #undef DRS_SIMT_CASE
   return DRS_OK;

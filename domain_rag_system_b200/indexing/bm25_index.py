@@ -27,11 +27,11 @@ from .. import _lib
 
 
 def choose_tile_docs(n_docs: int, sm_count: int = 148) -> int:
-    """Documents per tile (power of two, 256..8192).  Large tiles amortise the per-(tile, query)
-    costs (zeroing, range lookup, scan) and are the default; small corpora get smaller tiles so a
-    single query still spreads over ~64 CTAs."""
+    """Documents per tile (power of two, 256..8192).  Every (tile, query) pair pays a fixed ~7 us of
+    barriers and dependent loads, so tiles are as large as shared memory allows (8192) unless the shard is
+    so small that even a single query could not spread over a handful of CTAs."""
     t = 8192
-    while t > 256 and n_docs // t < 64:
+    while t > 256 and n_docs // t < 8:
         t //= 2
     return t
 

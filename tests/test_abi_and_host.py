@@ -96,7 +96,8 @@ def test_string_corpus_build_assigns_ids_in_first_appearance_order():
 
 def test_tile_size_choice():
     assert choose_tile_docs(600) == 256
-    assert choose_tile_docs(100_000) == 1024
+    assert choose_tile_docs(20_000) == 2048
+    assert choose_tile_docs(100_000) == 8192
     assert choose_tile_docs(1_000_000) == 8192
     assert choose_tile_docs(10_000_000) == 8192
 
