@@ -207,7 +207,17 @@ def run_reference(args):
 
 
 def workload_config(args):
-    return {"workload": f"BASELINE configs[1]: {args.chunks} chunks x {EMB_DIM}-d bf16, {args.queries}-query batch, "
+    if args.chunks == 1_000_000 and args.fusion == "rrf" and args.top_k == 5 and not args.rerank_top_n:
+        name = "configs[1]"
+    elif args.chunks == 10_000_000 and args.fusion == "weighted" and args.rerank_top_n == 30:
+        name = "configs[2]"
+    elif args.chunks >= 100_000_000 and args.top_k == 10:
+        name = "configs[3]"
+    elif args.chunks == 10_000_000 and args.rerank_top_n == 50:
+        name = "configs[4] (latency mode)"
+    else:
+        name = "custom"
+    return {"workload": f"BASELINE {name}: {args.chunks} chunks x {EMB_DIM}-d bf16, {args.queries}-query batch, "
                         f"top_k={args.top_k}, {args.fusion.upper()} fusion, BM25 Zipf(s=1.07) vocab {args.vocab}",
             "chunks": args.chunks, "queries_per_step": args.queries, "top_k": args.top_k, "kprime": 2 * args.top_k,
             "fusion": args.fusion, "rerank_top_n": args.rerank_top_n, "dim": EMB_DIM, "vocab": args.vocab,
@@ -323,13 +333,18 @@ def run_ours(args):
     d_ms, d_n = prof["dense_select"]
     flops = 2.0 * args.queries * n_local * EMB_DIM
     dense_tflops = flops / (d_ms / max(d_n, 1) / 1e3) / 1e12 if d_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_bm25 = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("dense_select_bytes_per_launch")
+            tj = json.load(f)
+        # ncu dram bytes were captured on the default workload; they do not transfer to other shapes
+        wl = tj.get("workload", {})
+        if world == 1 and all(wl.get(k) == getattr(args, k) for k in ("chunks", "queries", "top_k", "fusion", "vocab")):
+            traffic = tj.get("dense_select_bytes_per_launch")
+            traffic_bm25 = tj.get("bm25_select_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "dense_umma_kernel" if _lib.load().drs_dense_last_kernel() == 2 else "dense_simt_kernel",
+    roofline_dense = {"kernel": "dense_umma_kernel" if _lib.load().drs_dense_last_kernel() == 2 else "dense_simt_kernel",
                 "bound": "tensor", "achieved": dense_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
                 "frac": dense_tflops / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
                 "frac_of_nominal_2250": dense_tflops / 2250.0, "flops_per_launch": flops,
@@ -339,9 +354,12 @@ def run_ours(args):
     bm_bytes = 8.0 * sum_df
     bm_gbs = bm_bytes / (b_ms / max(b_n, 1) / 1e3) / 1e9 if b_ms > 0 else 0.0
     roofline_bm25 = {"kernel": "bm25_select_kernel", "bound": "hbm", "achieved": bm_gbs, "peak": peaks["hbm_gbs"],
-                     "unit": "GB/s", "frac": bm_gbs / peaks["hbm_gbs"], "bytes_per_launch": bm_bytes,
+                     "unit": "GB/s", "frac": bm_gbs / peaks["hbm_gbs"], "traffic": traffic_bm25,
+                     "peak_source": peaks["source"], "bytes_per_launch": bm_bytes,
                      "sum_df_per_batch": sum_df, "ms_per_launch": b_ms / max(b_n, 1)}
     breakdown = {k: (v[0] / args.steps) for k, v in prof.items()}
+    # `roofline` describes whichever selection kernel takes the larger share of the step
+    roofline = roofline_bm25 if b_ms > d_ms else roofline_dense
 
     # ---- latency mode: sequential single-query calls (BASELINE configs[4]) ---------------------------
     latency = None
@@ -404,7 +422,8 @@ def run_ours(args):
         "data": "synthetic", "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches, "roofline": roofline, "roofline_bm25": roofline_bm25,
+        "gpu_launches": launches, "roofline": roofline, "roofline_dense": roofline_dense,
+        "roofline_bm25": roofline_bm25,
         "kernel_ms_per_step": breakdown, "cpu_baseline": cpu_baseline, "parity": recall, "clocks": clocks,
         "latency": latency,
     }
