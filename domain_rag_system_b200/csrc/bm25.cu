@@ -27,6 +27,8 @@
 // Stage 2 (bm25_rescore): the kk surviving candidates per query are re-scored in fp64 with
 // rank_bm25's exact operation order (tf looked up by binary search), sorted by
 // (score desc, doc desc), and the first k' are emitted.
+#include <climits>
+
 #include "common.cuh"
 
 namespace drs {
@@ -44,18 +46,17 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     unsigned long long* __restrict__ gtau) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
-  float* sc = reinterpret_cast<float*>(mbuf + BM25_MBUF);                // [tile_docs]
+  int32_t* sc = reinterpret_cast<int32_t*>(mbuf + BM25_MBUF);            // [tile_docs] fixed-point scores
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
-  __shared__ long long s_a[BM25_TCHUNK], s_e[BM25_TCHUNK];  // posting ranges of the staged terms in this tile
   __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
-  __shared__ int s_drow[BM25_TCHUNK], s_sidx[BM25_TCHUNK];   // compacted: dense rows / indices of non-empty posting ranges
-  __shared__ int s_nd, s_ns;
+  __shared__ int s_drow[BM25_TCHUNK];                        // compacted dense rows, query order
+  __shared__ int s_nd;
   __shared__ int s_term[BM25_TCHUNK];
   __shared__ long long s_base[BM25_TCHUNK];
 
   const int T = ix.tile_docs;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile_hi = min(ix.n_tiles, (int(blockIdx.x) + 1) * tiles_per_cta) - 1;
   const int tile_lo = int(blockIdx.x) * tiles_per_cta;
   const int cap = BM25_MBUF - kk;
@@ -113,6 +114,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
     const bool one_chunk = (t1 - t0) <= BM25_TCHUNK;
+    // Stored impacts are at most 2^26 in magnitude; with more than 16 token occurrences they are shifted
+    // down so that no document's sum can leave the signed 31-bit range.  The shift depends on the query
+    // alone, so scores stay comparable across tiles, CTAs and shards of the launch.
+    int sh = 0;
+    while ((16 << sh) < t1 - t0) ++sh;   // (t1 - t0) * 2^(26 - sh) <= 2^30
     long long seen = 0;   // documents scanned so far for this (slice, query)
     if (one_chunk) stage_terms(t0, t1 - t0);
     for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
@@ -126,151 +132,111 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       const int64_t doc0 = int64_t(j) * T;
       const int64_t rem = ix.n_docs - doc0;
       const int tile_n = rem < int64_t(T) ? int(rem) : T;
+      const uint32_t d0u = uint32_t(doc0);  // tile-local index = document id - d0u
       // ---- accumulate ---------------------------------------------------------------------
-      // Order of the fp32 additions into a document's score: the query's head (dense-row) terms first,
-      // in query order, then its postings-list terms in query order.  The order is the same for every
-      // document, so documents with identical (term, impact) patterns still get identical sums.
-      // The ranges [a, e) of every staged term inside this tile are fetched by separate threads in one
-      // go (term id -> term offset -> tile pointer is a chain of dependent loads; paying it once per
-      // tile instead of once per term keeps the loops below on streaming loads only).
+      // Scores are integer sums of fixed-point impacts, so the order of the additions is free: the head
+      // terms' dense rows are added by the thread that owns the documents (plain read-modify-write, the
+      // first sweep also initialises the tile), then the other terms' postings are added with shared-
+      // memory integer atomics by whichever warp picks the postings up -- no barrier between terms.
       bool tile_init = false;   // false: the tile still holds the previous query's scores
       for (int c0 = t0; c0 < t1; c0 += BM25_TCHUNK) {
         const int nstaged = min(BM25_TCHUNK, t1 - c0);
         if (!one_chunk) stage_terms(c0, nstaged);   // long queries: term metadata is restaged per tile
-        // this tile's posting ranges of the postings-list terms (one dependent load per term)
-        if (tid < nstaged) {
-          const long long base = s_base[tid];
-          long long a = 0, e = 0;
-          if (base >= 0) {
-            const uint32_t* tp = ix.d_tile_ptr + size_t(s_term[tid]) * (ix.n_tiles + 1) + j;
-            a = base + tp[0];
-            e = base + tp[1];
-          }
-          s_a[tid] = a;
-          s_e[tid] = e;
+        // Every warp fetches the posting ranges of the first 32 staged terms inside this tile for itself
+        // (term id -> tile pointer is a dependent load; issued here, consumed after the dense sweeps).
+        uint32_t tp0 = 0, tp1 = 0;
+        if (lane < nstaged && s_base[lane] >= 0) {
+          const uint32_t* tp = ix.d_tile_ptr + size_t(s_term[lane]) * (ix.n_tiles + 1) + j;
+          tp0 = __ldg(tp);
+          tp1 = __ldg(tp + 1);
         }
-        __syncthreads();
-        if (tid < 32) {   // warp 0 compacts the indices of the non-empty ranges, keeping query order
-          int ns = 0;
-          for (int b0 = 0; b0 < nstaged; b0 += 32) {
-            const int i = b0 + tid;
-            const bool f = i < nstaged && s_a[i] < s_e[i];
-            const unsigned m = __ballot_sync(0xffffffffu, f);
-            if (f) s_sidx[ns + __popc(m & ((1u << tid) - 1u))] = i;
-            ns += __popc(m);
-          }
-          if (tid == 0) s_ns = ns;
-        }
-        __syncthreads();
-        const int nd = s_nd, ns = s_ns;
+        const int nd = s_nd;
         // -- pass A: dense rows, up to four fused per sweep; the first sweep also initialises the tile
-        float4* dst = reinterpret_cast<float4*>(sc);
+        int4* dst = reinterpret_cast<int4*>(sc);
         for (int g0 = 0; g0 < nd; g0 += 4) {
           const int ng = min(4, nd - g0);
-          const float4* r0 = reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
-          const float4* r1 = ng > 1 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
-          const float4* r2 = ng > 2 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
-          const float4* r3 = ng > 3 ? reinterpret_cast<const float4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int4* r0 = reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
+          const int4* r1 = ng > 1 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
+          const int4* r2 = ng > 2 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
+          const int4* r3 = ng > 3 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
+          const int4 z = make_int4(0, 0, 0, 0);
           for (int i = tid; i < T / 4; i += 2 * BM25_THREADS) {
             const int i2 = i + BM25_THREADS;
             const bool two = i2 < T / 4;
-            const float4 a0 = __ldg(r0 + i), a1 = ng > 1 ? __ldg(r1 + i) : z, a2 = ng > 2 ? __ldg(r2 + i) : z,
-                         a3 = ng > 3 ? __ldg(r3 + i) : z;
-            const float4 b0 = two ? __ldg(r0 + i2) : z, b1 = (two && ng > 1) ? __ldg(r1 + i2) : z,
-                         b2 = (two && ng > 2) ? __ldg(r2 + i2) : z, b3 = (two && ng > 3) ? __ldg(r3 + i2) : z;
-            float4 x = tile_init ? dst[i] : z;
-            x.x += a0.x; x.y += a0.y; x.z += a0.z; x.w += a0.w;
-            if (ng > 1) { x.x += a1.x; x.y += a1.y; x.z += a1.z; x.w += a1.w; }
-            if (ng > 2) { x.x += a2.x; x.y += a2.y; x.z += a2.z; x.w += a2.w; }
-            if (ng > 3) { x.x += a3.x; x.y += a3.y; x.z += a3.z; x.w += a3.w; }
+            const int4 a0 = __ldg(r0 + i), a1 = ng > 1 ? __ldg(r1 + i) : z, a2 = ng > 2 ? __ldg(r2 + i) : z,
+                       a3 = ng > 3 ? __ldg(r3 + i) : z;
+            const int4 b0 = two ? __ldg(r0 + i2) : z, b1 = (two && ng > 1) ? __ldg(r1 + i2) : z,
+                       b2 = (two && ng > 2) ? __ldg(r2 + i2) : z, b3 = (two && ng > 3) ? __ldg(r3 + i2) : z;
+            int4 x = tile_init ? dst[i] : z;
+            x.x += (a0.x >> sh) + (a1.x >> sh) + (a2.x >> sh) + (a3.x >> sh);
+            x.y += (a0.y >> sh) + (a1.y >> sh) + (a2.y >> sh) + (a3.y >> sh);
+            x.z += (a0.z >> sh) + (a1.z >> sh) + (a2.z >> sh) + (a3.z >> sh);
+            x.w += (a0.w >> sh) + (a1.w >> sh) + (a2.w >> sh) + (a3.w >> sh);
             dst[i] = x;
             if (two) {
-              float4 y = tile_init ? dst[i2] : z;
-              y.x += b0.x; y.y += b0.y; y.z += b0.z; y.w += b0.w;
-              if (ng > 1) { y.x += b1.x; y.y += b1.y; y.z += b1.z; y.w += b1.w; }
-              if (ng > 2) { y.x += b2.x; y.y += b2.y; y.z += b2.z; y.w += b2.w; }
-              if (ng > 3) { y.x += b3.x; y.y += b3.y; y.z += b3.z; y.w += b3.w; }
+              int4 y = tile_init ? dst[i2] : z;
+              y.x += (b0.x >> sh) + (b1.x >> sh) + (b2.x >> sh) + (b3.x >> sh);
+              y.y += (b0.y >> sh) + (b1.y >> sh) + (b2.y >> sh) + (b3.y >> sh);
+              y.z += (b0.z >> sh) + (b1.z >> sh) + (b2.z >> sh) + (b3.z >> sh);
+              y.w += (b0.w >> sh) + (b1.w >> sh) + (b2.w >> sh) + (b3.w >> sh);
               dst[i2] = y;
             }
           }
-          tile_init = true;
-          __syncthreads();
+          tile_init = true;   // the same thread owns the same documents in every sweep: no barrier between sweeps
         }
         if (!tile_init) {
-          for (int i = tid; i < T / 4; i += BM25_THREADS) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = tid; i < T / 4; i += BM25_THREADS) dst[i] = make_int4(0, 0, 0, 0);
           tile_init = true;
-          __syncthreads();
         }
-        // -- pass B: postings-list terms, one per barrier; the first 4 postings per thread of the NEXT
-        // term are fetched before the barrier of the current one
-        const uint32_t d0u = uint32_t(doc0);  // tile-local index = document id - d0u
-        uint4 pd = make_uint4(0, 0, 0, 0);
-        float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto prefetch = [&](int k) {   // first vector group of sparse term k (if this thread has one)
-          if (k < ns) {
-            const int64_t a = s_a[s_sidx[k]], e = s_e[s_sidx[k]];
-            int64_t a4 = (a + 3) & ~int64_t(3);
-            if (a4 > e) a4 = e;
-            if (tid < ((e - a4) >> 2)) {
-              pd = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + a4) + tid);
-              pi = __ldg(reinterpret_cast<const float4*>(ix.d_post_impact + a4) + tid);
+        __syncthreads();   // the tile is initialised: atomics from any warp may follow
+        // -- pass B: postings-list terms.  Rounds of 32 staged terms; inside a round the terms' postings are
+        // cut into chunks of 128 (aligned groups of four per lane) and the warps take chunks round-robin.
+        for (int r0 = 0; r0 < nstaged; r0 += 32) {
+          if (r0 > 0) {   // rounds after the first fetch their ranges here
+            tp0 = tp1 = 0;
+            if (r0 + lane < nstaged && s_base[r0 + lane] >= 0) {
+              const uint32_t* tp = ix.d_tile_ptr + size_t(s_term[r0 + lane]) * (ix.n_tiles + 1) + j;
+              tp0 = __ldg(tp);
+              tp1 = __ldg(tp + 1);
             }
           }
-        };
-        prefetch(0);
-        for (int k = 0; k < ns; ++k) {
-          const int64_t a = s_a[s_sidx[k]], e = s_e[s_sidx[k]];
-          // head (to 16-byte alignment), vector body (4 postings per thread per load), tail.  Inside one
-          // term every document occurs once, so the read-modify-writes of a batch never alias: all loads
-          // are issued before the adds and stores.
-          int64_t a4 = (a + 3) & ~int64_t(3);
-          if (a4 > e) a4 = e;
-          const int64_t nvec = (e - a4) >> 2;
-          const uint4 d0 = pd;
-          const float4 i0 = pi;
-          const bool have0 = tid < nvec;
-          // tail / head / further groups of this term, then the next term's first group
-          uint32_t hd = 0, td = 0;
-          float hi = 0.f, tl = 0.f;
-          const bool haveh = a + tid < a4;
-          const int64_t ts = a4 + (nvec << 2);
-          const bool havet = ts + tid < e;
-          if (haveh) {
-            hd = __ldg(ix.d_post_doc + a + tid);
-            hi = __ldg(ix.d_post_impact + a + tid);
+          long long a4 = 0;      // first posting of my term in this tile, rounded down to a group of four
+          int lo = 0, len4 = 0;  // postings [a4+lo, a4+len4) are the term's
+          if (tp1 > tp0) {
+            const long long a = s_base[r0 + lane] + tp0;
+            a4 = a & ~3ll;
+            lo = int(a - a4);
+            len4 = lo + int(tp1 - tp0);
           }
-          if (havet) {
-            td = __ldg(ix.d_post_doc + ts + tid);
-            tl = __ldg(ix.d_post_impact + ts + tid);
+          const int nch = (len4 + 127) >> 7;
+          int incl = nch;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
           }
-          prefetch(k + 1);
-          if (have0) {
-            const float v0 = sc[d0.x - d0u], v1 = sc[d0.y - d0u], v2 = sc[d0.z - d0u], v3 = sc[d0.w - d0u];
-            sc[d0.x - d0u] = v0 + i0.x;
-            sc[d0.y - d0u] = v1 + i0.y;
-            sc[d0.z - d0u] = v2 + i0.z;
-            sc[d0.w - d0u] = v3 + i0.w;
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          const int cstart = incl - nch;
+          for (int c = warp; c < total; c += BM25_THREADS / 32) {
+            const unsigned m = __ballot_sync(0xffffffffu, c >= cstart && c < incl);   // exactly one lane owns chunk c
+            const int src = __ffs(m) - 1;
+            const long long sa4 = __shfl_sync(0xffffffffu, a4, src);
+            const int slo = __shfl_sync(0xffffffffu, lo, src), slen = __shfl_sync(0xffffffffu, len4, src);
+            const int off = ((c - __shfl_sync(0xffffffffu, cstart, src)) << 7) + (lane << 2);
+            if (off < slen) {
+              const uint4 d = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + sa4 + off));
+              const int4 im = __ldg(reinterpret_cast<const int4*>(ix.d_post_impact + sa4 + off));
+              if (off >= slo) atomicAdd(sc + (d.x - d0u), im.x >> sh);
+              if (off + 1 >= slo && off + 1 < slen) atomicAdd(sc + (d.y - d0u), im.y >> sh);
+              if (off + 2 >= slo && off + 2 < slen) atomicAdd(sc + (d.z - d0u), im.z >> sh);
+              if (off + 3 >= slo && off + 3 < slen) atomicAdd(sc + (d.w - d0u), im.w >> sh);
+            }
           }
-          const uint4* dv = reinterpret_cast<const uint4*>(ix.d_post_doc + a4);
-          const float4* iv = reinterpret_cast<const float4*>(ix.d_post_impact + a4);
-          for (int64_t v = tid + BM25_THREADS; v < nvec; v += BM25_THREADS) {
-            const uint4 d1 = __ldg(dv + v);
-            const float4 i1 = __ldg(iv + v);
-            const float v0 = sc[d1.x - d0u], v1 = sc[d1.y - d0u], v2 = sc[d1.z - d0u], v3 = sc[d1.w - d0u];
-            sc[d1.x - d0u] = v0 + i1.x;
-            sc[d1.y - d0u] = v1 + i1.y;
-            sc[d1.z - d0u] = v2 + i1.z;
-            sc[d1.w - d0u] = v3 + i1.w;
-          }
-          if (haveh) sc[hd - d0u] += hi;
-          if (havet) sc[td - d0u] += tl;
-          __syncthreads();
         }
-        __syncthreads();  // the staging arrays may be rewritten
+        __syncthreads();  // all postings of this chunk of terms are in; the staging arrays may be rewritten
       }
       if (!tile_init) {   // query without terms: every score is 0
-        for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<float4*>(sc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<int4*>(sc)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
       }
       // ---- scan the tile, highest document first -----------------------------------------
@@ -280,17 +246,17 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       // merge, so the first sort is small; a warm CTA sweeps the rest of the tile in one go.
       auto scan_range = [&](int from, int count) {   // documents T-1-from downwards
         const unsigned long long tau = s_tau;
-        const float tau_s = tau == 0 ? -INFINITY : key_score(tau);
+        const int tau_s = tau == 0 ? INT_MIN : key_fx(tau);
         for (int g = 4 * tid; g < count && from + g < T; g += 4 * BM25_THREADS) {
           const int hi = T - 1 - from - g;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
-          const float4 v = *reinterpret_cast<const float4*>(sc + hi - 3);
-          if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tau_s) {
-            const float vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
+          const int4 v = *reinterpret_cast<const int4*>(sc + hi - 3);
+          if (max(max(v.x, v.y), max(v.z, v.w)) >= tau_s) {
+            const int vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int dl = hi - u;
               if (vs[u] >= tau_s && dl < tile_n) {
-                const uint64_t key = make_key(vs[u], uint32_t(doc0 + dl));
+                const uint64_t key = make_key_fx(vs[u], uint32_t(doc0 + dl));
                 if (key > tau) {
                   const int pos = atomicAdd(&s_cnt, 1);
                   if (pos < cap) mbuf[kk + pos] = key;

@@ -71,6 +71,12 @@ __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row)
 }
 __host__ __device__ __forceinline__ float key_score(uint64_t k) { return unord32(uint32_t(k >> 32)); }
 __host__ __device__ __forceinline__ uint32_t key_row(uint64_t k) { return uint32_t(k); }
+// fixed-point (signed integer) scores: same (score desc, row desc) order, 0 stays "empty" because the
+// BM25 scale keeps |score| < 2^31
+__host__ __device__ __forceinline__ uint64_t make_key_fx(int32_t score, uint32_t row) {
+  return (uint64_t(uint32_t(score) ^ 0x80000000u) << 32) | row;
+}
+__host__ __device__ __forceinline__ int32_t key_fx(uint64_t k) { return int32_t(uint32_t(k >> 32) ^ 0x80000000u); }
 
 __device__ __forceinline__ uint64_t ord64(double d) {
   uint64_t u = (uint64_t)__double_as_longlong(d + 0.0);

@@ -9,7 +9,8 @@ reference ``src/indexing/bm25_indexer.py:102-106``), laid out for the CUDA kerne
   ``average_idf``; negative idfs are replaced by ``epsilon * average_idf``;
 * ``doc_kd[d] = k1 * (1 - b + b * doc_len[d] / avgdl)`` in fp64, same operation order;
 * postings sorted by (term, doc): ``post_doc`` u32, ``post_tf`` u16,
-  ``post_impact`` = fp32(idf * tf*(k1+1) / (tf + doc_kd[doc]));
+  ``post_impact`` = int32 fixed point round(idf * tf*(k1+1) / (tf + doc_kd[doc]) * 2^s) with
+  ``max |impact| * 2^s <= 2^26`` (``impact_scale_log2``); head terms also get dense rows of them;
 * ``tile_ptr[t, j]`` = first posting of term t whose doc >= j*tile_docs (relative).
 
 The construction uses torch ops so it runs on the GPU for large corpora (sort-based CSR
@@ -24,6 +25,13 @@ import numpy as np
 import torch
 
 from .. import _lib
+
+IMPACT_BITS = 26   # |stored impact| <= 2^26: 16 query tokens sum without a shift (csrc/bm25.cu)
+POST_PAD = 4       # zeroed entries after the last posting (aligned 4-wide reads)
+
+
+def _pad_tail(t: torch.Tensor) -> torch.Tensor:
+    return torch.cat([t, torch.zeros(POST_PAD, dtype=t.dtype, device=t.device)])
 
 
 def choose_tile_docs(n_docs: int, sm_count: int = 148) -> int:
@@ -53,6 +61,7 @@ class Bm25DeviceIndex:
         self.n_docs_global = 0
         self.total_tokens = 0
         self.n_dense = 0                           # head terms that also have a dense impact row
+        self.impact_scale_log2 = 0                 # stored impacts = round(impact * 2^s)
         self.t: Dict[str, torch.Tensor] = {}       # device tensors
         self._struct = None
 
@@ -152,7 +161,15 @@ class Bm25DeviceIndex:
         kd = torch.from_numpy(kd_h).to(build_device)
         idf_d = torch.from_numpy(idf).to(build_device)
         tf64 = tf.to(torch.float64)
-        impact = (idf_d[post_term] * (tf64 * (self.k1 + 1) / (tf64 + kd[post_doc]))).to(torch.float32)
+        impact64 = idf_d[post_term] * (tf64 * (self.k1 + 1) / (tf64 + kd[post_doc]))
+        # Pre-selection works on INTEGER sums of fixed-point impacts (order-free, so ties are exact):
+        # scale 2^s with max |impact| * 2^s <= 2^IMPACT_BITS.  idf is global, so the bound and therefore
+        # the scale are the same on every shard of a sharded corpus.
+        max_imp = float(np.abs(idf).max()) * (self.k1 + 1)
+        self.impact_scale_log2 = int(min(40, math.floor(IMPACT_BITS - math.log2(max_imp)))) if max_imp > 0 else 0
+        impact = torch.round(impact64 * float(2.0 ** self.impact_scale_log2)).clamp_(-2 ** IMPACT_BITS, 2 ** IMPACT_BITS)
+        impact = impact.to(torch.int32)
+        del impact64
         if int(tf.max()) > 65535:
             raise NotImplementedError("term frequency above 65535 in one chunk")
         # per-tile offsets
@@ -171,7 +188,7 @@ class Bm25DeviceIndex:
         heavy = torch.nonzero(df >= max(1.0, dense_frac * n)).flatten()
         if heavy.numel() > max_dense_terms:
             heavy = heavy[torch.argsort(df[heavy], descending=True)[:max_dense_terms]]
-        dense_impact = torch.zeros(max(int(heavy.numel()), 1), n_pad, dtype=torch.float32, device=build_device)
+        dense_impact = torch.zeros(max(int(heavy.numel()), 1), n_pad, dtype=torch.int32, device=build_device)
         if heavy.numel() and dense_frac > 0:
             dense_slot[heavy] = torch.arange(heavy.numel(), dtype=torch.int32, device=build_device)
             slot_of_post = dense_slot[post_term]
@@ -185,8 +202,9 @@ class Bm25DeviceIndex:
             "dense_slot": dense_slot.to(device),
             "dense_impact": dense_impact.to(device),
             "term_offsets": term_offsets.to(device),
-            "post_doc": post_doc.to(torch.int32).to(device),      # bit pattern of u32 (n < 2^31 enforced below)
-            "post_impact": impact.to(device),
+            # postings are read in aligned groups of four: POST_PAD zeroed entries follow the last posting
+            "post_doc": _pad_tail(post_doc.to(torch.int32)).to(device),   # bit pattern of u32 (n < 2^31 enforced below)
+            "post_impact": _pad_tail(impact).to(device),
             "post_tf": tf.to(torch.int16).to(device),             # bit pattern of u16
             "tile_ptr": tile_ptr.to(torch.int32).contiguous().to(device),
             "idf": idf_d.to(device),
@@ -224,7 +242,7 @@ class Bm25DeviceIndex:
         if self._struct is None:
             s = _lib.Bm25IndexStruct()
             s.n_docs, s.n_terms, s.tile_docs, s.n_tiles, s.reserved = (self.n_docs, self.n_terms, self.tile_docs,
-                                                                       self.n_tiles, 0)
+                                                                       self.n_tiles, self.impact_scale_log2)
             t = self.t
             s.d_term_offsets = t["term_offsets"].data_ptr()
             s.d_post_doc = t["post_doc"].data_ptr()
@@ -246,7 +264,7 @@ class Bm25DeviceIndex:
 
     @property
     def nnz(self):
-        return int(self.t["post_doc"].numel())
+        return int(self.t["post_doc"].numel()) - POST_PAD
 
     def encode_queries(self, queries: Sequence[Sequence], pinned: bool = False):
         """Token strings (or term ids) -> (q_terms int32, q_offsets int32) HOST tensors.
@@ -280,6 +298,7 @@ class Bm25DeviceIndex:
                              k1=self.k1, b=self.b, epsilon=self.epsilon, avgdl=self.avgdl,
                              average_idf=self.average_idf, vocab_present=self.vocab_present,
                              total_tokens=self.total_tokens, row_offset=self.row_offset,
+                             impact_scale_log2=self.impact_scale_log2, n_dense=self.n_dense,
                              n_docs_global=self.n_docs_global),
                 "vocab": self.vocab, "tensors": {k: v.cpu() for k, v in self.t.items()}}
 

@@ -91,10 +91,12 @@ typedef struct drs_bm25_index {
   int32_t n_terms;              /* V                                                     */
   int32_t tile_docs;            /* documents per tile, power of two, 256..8192          */
   int32_t n_tiles;              /* ceil(N / tile_docs)                                   */
-  int32_t reserved;
+  int32_t impact_scale_log2;    /* s: stored impacts are round(impact * 2^s), |value| <= 2^26 */
   const int64_t* d_term_offsets;/* [V+1] postings range of each term                     */
   const uint32_t* d_post_doc;   /* [nnz] document id, ascending inside a term            */
-  const float* d_post_impact;   /* [nnz] fp32(idf*tf*(k1+1)/(tf+kd[doc]))                */
+  const int32_t* d_post_impact; /* [nnz] fixed point: round(idf*tf*(k1+1)/(tf+kd[doc]) * 2^s).
+                                   d_post_doc / d_post_impact are read in aligned groups of four:
+                                   allocate (and zero) 4 entries beyond nnz                */
   const uint16_t* d_post_tf;    /* [nnz] term frequency (saturated at 65535)             */
   const uint32_t* d_tile_ptr;   /* [V*(n_tiles+1)] first posting of term t with doc >=
                                    j*tile_docs, relative to d_term_offsets[t]            */
@@ -103,9 +105,12 @@ typedef struct drs_bm25_index {
   double k1_plus_1;             /* k1 + 1                                                */
   /* Head terms (present in a large fraction of the documents) additionally carry a DENSE row of
      per-document impacts: adding a row is a vector add (4 bytes/document, no scatter).  The
-     values are the same fp32 impacts, 0 where the term is absent, so scores are unchanged.    */
+     values are the same fixed-point impacts, 0 where the term is absent, so scores are unchanged.
+     Pre-selection scores are INTEGER sums of these impacts: integer addition is associative, so a
+     document's pre-selection score does not depend on the order its terms are visited in and
+     documents with the same (term, impact) multiset tie exactly, as they do in the reference.  */
   const int32_t* d_dense_slot;  /* [V] row of the term in d_dense_impact, -1 = sparse only; may be NULL */
-  const float* d_dense_impact;  /* [n_dense, dense_stride]                               */
+  const int32_t* d_dense_impact;/* [n_dense, dense_stride] fixed point, same scale       */
   int64_t dense_stride;         /* n_tiles * tile_docs (rows are zero padded)            */
 } drs_bm25_index;
 

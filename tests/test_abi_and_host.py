@@ -66,7 +66,10 @@ def test_host_index_build_matches_oracle(n, vocab):
     assert ix.avgdl == orc.avgdl and ix.average_idf == orc.average_idf
     assert np.array_equal(ix.t["idf"].numpy(), orc.idf)
     assert np.array_equal(ix.t["term_offsets"].numpy(), orc.term_offsets)
-    assert np.array_equal(ix.t["post_doc"].numpy().astype(np.int64), orc.post_doc)
+    nnz = ix.nnz
+    assert nnz == orc.post_doc.size and ix.t["post_doc"].numel() == nnz + 4   # 4 zeroed pad entries
+    assert not ix.t["post_doc"][nnz:].any() and not ix.t["post_impact"][nnz:].any()
+    assert np.array_equal(ix.t["post_doc"].numpy()[:nnz].astype(np.int64), orc.post_doc)
     assert np.array_equal(ix.t["post_tf"].numpy().astype(np.int64), orc.post_tf)
     kd = 1.5 * (1 - 0.75 + 0.75 * orc.doc_len / orc.avgdl)
     assert np.array_equal(ix.t["doc_kd"].numpy(), kd)
@@ -76,10 +79,13 @@ def test_host_index_build_matches_oracle(n, vocab):
         docs = orc.post_doc[orc.term_offsets[t]:orc.term_offsets[t + 1]]
         want = np.searchsorted(docs, np.arange(ix.n_tiles + 1) * ix.tile_docs, side="left")
         assert np.array_equal(tp[t], want)
-    # fp32 impacts are the rounded fp64 contributions
+    # stored impacts are the fp64 contributions in fixed point: round(impact * 2^s), |.| <= 2^26
     t_of = np.repeat(np.arange(vocab), np.diff(orc.term_offsets))
     imp = orc.idf[t_of] * (orc.post_tf * 2.5 / (orc.post_tf + kd[orc.post_doc]))
-    assert np.allclose(ix.t["post_impact"].numpy(), imp.astype(np.float32), rtol=1e-6, atol=0)
+    s = ix.impact_scale_log2
+    fx = ix.t["post_impact"].numpy()[:nnz].astype(np.int64)
+    assert np.abs(fx).max() <= 2 ** 26 and np.abs(orc.idf).max() * 2.5 * 2.0 ** (s + 1) > 2 ** 26
+    assert np.abs(fx - imp * 2.0 ** s).max() <= 0.5
 
 
 def test_string_corpus_build_assigns_ids_in_first_appearance_order():
@@ -113,7 +119,7 @@ def test_dense_head_term_rows_match_postings():
     assert dense.shape[1] == ix.n_tiles * ix.tile_docs
     to, pd, pi = ix.t["term_offsets"].numpy(), ix.t["post_doc"].numpy(), ix.t["post_impact"].numpy()
     for t in np.flatnonzero(slot >= 0):
-        row = np.zeros(dense.shape[1], dtype=np.float32)
+        row = np.zeros(dense.shape[1], dtype=np.int32)
         row[pd[to[t]:to[t + 1]]] = pi[to[t]:to[t + 1]]
         assert np.array_equal(dense[slot[t]], row)
     off = Bm25DeviceIndex.from_token_ids(offs, toks, 60, device="cpu", tile_docs=256, dense_frac=0.0)
