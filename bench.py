@@ -324,6 +324,15 @@ def run_ours(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     ms_e2e = timed(step_e2e, args.steps)
 
+    # exactness bookkeeping (outside the timed region): how many queries each retriever PROVED exact on its fast
+    # path and how many it had to escalate
+    kp = 2 * fetch_k
+    _, _, bflags = _lib.bm25_topk(ix.struct(), q_terms_d, q_offs_d, args.queries, kp, want_flags=True)
+    _, _, dflags = _lib.dense_topk(qv_d, emb, inv, kp, kernel=kernel)
+    exactness = {"bm25_proven": int((bflags == 0).sum()), "bm25_escalated": int((bflags == 2).sum()),
+                 "dense_proven": int((dflags == 0).sum()), "dense_escalated": int((dflags >= 2).sum()),
+                 "dense_unproven": int((dflags == 1).sum()), "queries": args.queries}
+
     ms_step = ms_total / args.steps
     value = args.queries / (ms_step / 1e3)
     e2e_value = args.queries / (ms_e2e / args.steps / 1e3)
@@ -424,7 +433,8 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "roofline": roofline, "roofline_dense": roofline_dense,
         "roofline_bm25": roofline_bm25,
-        "kernel_ms_per_step": breakdown, "cpu_baseline": cpu_baseline, "parity": recall, "clocks": clocks,
+        "kernel_ms_per_step": breakdown, "cpu_baseline": cpu_baseline, "parity": recall, "exactness": exactness,
+        "clocks": clocks,
         "latency": latency,
     }
     print(json.dumps(line), flush=True)

@@ -42,6 +42,8 @@ EXPORTS = {
     "drs_dense_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "drs_bm25_workspace_bytes": (_sz, [_i32, C.POINTER(Bm25IndexStruct), _i32]),
     "drs_bm25_topk": (C.c_int, [C.POINTER(Bm25IndexStruct), _vp, _vp, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "drs_bm25_topk_ex": (C.c_int, [C.POINTER(Bm25IndexStruct), _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _sz,
+                                   _vp]),
     "drs_fuse_topk": (C.c_int, [_i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp]),
     "drs_rerank_cosine": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "drs_merge_candidates_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
@@ -161,9 +163,14 @@ def dense_topk(queries_f32, corpus_bf16, inv_norm, kprime, row_mask=None, kernel
     return scores, ids, flags
 
 
+BM25_MODES = {"auto": 0, "no_escalation": 1, "escalate_all": 2}
+
+
 def bm25_topk(index_struct: Bm25IndexStruct, q_terms, q_offsets, n_queries, kprime, ws: Workspace | None = None,
-              out=None):
-    """Returns (scores fp64 [Q,k'], ids int64 [Q,k'])."""
+              out=None, mode: str = "auto", want_flags: bool = False):
+    """Returns (scores fp64 [Q,k'], ids int64 [Q,k']) -- plus flags int32 [Q] with ``want_flags``:
+    0 = the integer pre-selection was proven exact, 2 = resolved by the exact escalation pass,
+    1 = unproven (only with mode "no_escalation")."""
     _need_cuda(q_terms, q_offsets)
     lib = load()
     dev = q_offsets.device
@@ -175,10 +182,12 @@ def bm25_topk(index_struct: Bm25IndexStruct, q_terms, q_offsets, n_queries, kpri
     ws = ws or Workspace()
     nbytes = lib.drs_bm25_workspace_bytes(n_queries, C.byref(index_struct), kprime)
     buf = ws.get(nbytes, dev)
+    flags = torch.empty(n_queries, dtype=torch.int32, device=dev) if want_flags else None
     with torch.cuda.device(dev):
-        _check(lib.drs_bm25_topk(C.byref(index_struct), _ptr(q_terms), _ptr(q_offsets), n_queries, kprime,
-                                 _ptr(scores), _ptr(ids), _ptr(buf), buf.numel(), _stream()))
-    return scores, ids
+        _check(lib.drs_bm25_topk_ex(C.byref(index_struct), _ptr(q_terms), _ptr(q_offsets), n_queries, kprime,
+                                    BM25_MODES[mode], _ptr(scores), _ptr(ids), _ptr(flags) if want_flags else None,
+                                    _ptr(buf), buf.numel(), _stream()))
+    return (scores, ids, flags) if want_flags else (scores, ids)
 
 
 def fuse_topk(mode, v_scores, v_ids, b_scores, b_ids, top_k, fusion_key=None, rrf_k=60.0, w_vector=0.5, w_bm25=0.5,

@@ -40,12 +40,57 @@ constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
 constexpr int BM25_MERGE_AT = 192;  // survivors that justify a re-sort (warm list): list + survivors fit a 256-sort
 constexpr int BM25_COLD_STEP = 128; // documents scanned before the first merge of a cold list
 
+// exact fp64 score of one document; rank_bm25 operation order:
+//   score += idf[t] * ( tf*(k1+1) / ( tf + k1*(1-b+b*dl/avgdl) ) )     for every query token occurrence
+__device__ __forceinline__ double bm25_exact_score(const drs_bm25_index& ix, const int32_t* __restrict__ q_terms,
+                                                   int t0, int t1, int64_t doc) {
+  const int j = int(doc / ix.tile_docs);
+  const double kd = ix.d_doc_kd[doc];
+  double score = 0.0;
+  for (int ti = t0; ti < t1; ++ti) {
+    const int t = q_terms[ti];
+    if (t < 0 || t >= ix.n_terms) continue;
+    const int64_t base = ix.d_term_offsets[t];
+    const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+    const int64_t end = base + tp[1];
+    int64_t lo = base + tp[0], hi = end;  // [lo, hi)
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (ix.d_post_doc[mid] < uint32_t(doc)) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < end && ix.d_post_doc[lo] == uint32_t(doc)) {
+      const double tf = double(ix.d_post_tf[lo]);
+      const double num = __dmul_rn(tf, ix.k1_plus_1);
+      const double den = __dadd_rn(tf, kd);
+      score = __dadd_rn(score, __dmul_rn(ix.d_idf[t], __ddiv_rn(num, den)));
+    }
+  }
+  return score;
+}
+
+// shift applied to the stored impacts of a query with nt token occurrences (see bm25_select_kernel)
+__host__ __device__ __forceinline__ int bm25_query_shift(int nt) {
+  int sh = 0;
+  while ((16 << sh) < nt) ++sh;   // nt * 2^(26 - sh) <= 2^30
+  return sh;
+}
+
+// EXACT = false: the pre-selection pass (integer scores, top-kk keys per (slice, query)).
+// EXACT = true : the escalation pass for the queries whose pre-selection could not be proven (flags[q] == 1):
+//   same accumulation, but EVERY document whose integer score reaches fx_low[q] -- the smallest integer score
+//   a member of the true top-k' can have, see bm25_rescore_kernel -- is re-scored exactly on the spot and the
+//   exact (score, doc) top-k' of the slice is kept.
+template <bool EXACT>
 __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
-    unsigned long long* __restrict__ gtau) {
+    unsigned long long* __restrict__ gtau, const int32_t* __restrict__ flags, const int32_t* __restrict__ fx_low,
+    int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
+  Pair64* pbuf = reinterpret_cast<Pair64*>(smem_raw);                    // EXACT: [BM25_MBUF / 2] (score, doc) pairs
+  __shared__ Pair64 s_kth;                                               // EXACT: current k'-th best pair
   int32_t* sc = reinterpret_cast<int32_t*>(mbuf + BM25_MBUF);            // [tile_docs] fixed-point scores
   __shared__ int s_cnt;
   __shared__ unsigned long long s_tau;
@@ -112,19 +157,27 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   };
 
   for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
+    if (EXACT && flags[q] != 1) continue;
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
     const bool one_chunk = (t1 - t0) <= BM25_TCHUNK;
     // Stored impacts are at most 2^26 in magnitude; with more than 16 token occurrences they are shifted
     // down so that no document's sum can leave the signed 31-bit range.  The shift depends on the query
     // alone, so scores stay comparable across tiles, CTAs and shards of the launch.
-    int sh = 0;
-    while ((16 << sh) < t1 - t0) ++sh;   // (t1 - t0) * 2^(26 - sh) <= 2^30
+    const int sh = bm25_query_shift(t1 - t0);
     long long seen = 0;   // documents scanned so far for this (slice, query)
     if (one_chunk) stage_terms(t0, t1 - t0);
-    for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
-    if (tid == 0) {
-      s_cnt = 0;
-      s_tau = *reinterpret_cast<volatile unsigned long long*>(gtau + q);
+    if constexpr (EXACT) {
+      for (int i = tid; i < kprime; i += BM25_THREADS) pbuf[i] = Pair64{0, -1};
+      if (tid == 0) {
+        s_cnt = 0;
+        s_kth = Pair64{0, -1};
+      }
+    } else {
+      for (int i = tid; i < kk; i += BM25_THREADS) mbuf[i] = 0;
+      if (tid == 0) {
+        s_cnt = 0;
+        s_tau = *reinterpret_cast<volatile unsigned long long*>(gtau + q);
+      }
     }
     __syncthreads();
 
@@ -239,83 +292,133 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<int4*>(sc)[i] = make_int4(0, 0, 0, 0);
         __syncthreads();
       }
-      // ---- scan the tile, highest document first -----------------------------------------
-      // Four consecutive documents per thread: one 16-byte shared load and a max test reject almost every
-      // group once the threshold is warm.  While this CTA has no threshold yet for the query (cold list,
-      // nothing published by other CTAs) only BM25_COLD_STEP documents are scanned before the first
-      // merge, so the first sort is small; a warm CTA sweeps the rest of the tile in one go.
-      auto scan_range = [&](int from, int count) {   // documents T-1-from downwards
-        const unsigned long long tau = s_tau;
-        const int tau_s = tau == 0 ? INT_MIN : key_fx(tau);
-        for (int g = 4 * tid; g < count && from + g < T; g += 4 * BM25_THREADS) {
-          const int hi = T - 1 - from - g;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
-          const int4 v = *reinterpret_cast<const int4*>(sc + hi - 3);
-          if (max(max(v.x, v.y), max(v.z, v.w)) >= tau_s) {
-            const int vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
+      if constexpr (EXACT) {
+        // ---- escalation: exact re-scoring of every document that can still belong to the top-k' ----
+        const int cap2 = BM25_MBUF / 2 - kprime;
+        const int fl = fx_low[q];
+        auto merge2 = [&]() {   // all threads; sorts list + appended pairs, keeps the best k'
+          const int n = kprime + min(s_cnt, cap2);
+          const int m = next_pow2(n);
+          for (int i = n + tid; i < m; i += BM25_THREADS) pbuf[i] = Pair64{0, -1};
+          __syncthreads();
+          block_bitonic_desc(pbuf, m, pair_less);
+          if (tid == 0) {
+            s_cnt = 0;
+            s_kth = pbuf[kprime - 1];
+          }
+          __syncthreads();
+        };
+        for (int seg = 0; seg < T; seg += BM25_THREADS) {
+          const int dl = T - 1 - seg - tid;   // highest document first
+          if (dl < tile_n && sc[dl] >= fl) {
+            const int64_t doc = doc0 + dl;
+            const Pair64 p{ord64(bm25_exact_score(ix, q_terms, t0, t1, doc)), doc};
+            if (pair_less(s_kth, p)) pbuf[kprime + atomicAdd(&s_cnt, 1)] = p;
+          }
+          __syncthreads();
+          if (s_cnt > cap2 - BM25_THREADS) merge2();
+        }
+        if (j == tile_lo) {
+          if (s_cnt > 0) merge2();
+        }
+      } else {
+        // ---- scan the tile, highest document first -----------------------------------------
+        // Four consecutive documents per thread: one 16-byte shared load and a max test reject almost every
+        // group once the threshold is warm.  While this CTA has no threshold yet for the query (cold list,
+        // nothing published by other CTAs) only BM25_COLD_STEP documents are scanned before the first
+        // merge, so the first sort is small; a warm CTA sweeps the rest of the tile in one go.
+        auto scan_range = [&](int from, int count) {   // documents T-1-from downwards
+          const unsigned long long tau = s_tau;
+          const int tau_s = tau == 0 ? INT_MIN : key_fx(tau);
+          for (int g = 4 * tid; g < count && from + g < T; g += 4 * BM25_THREADS) {
+            const int hi = T - 1 - from - g;   // my group is documents hi-3 .. hi (hi-3 is 4-aligned)
+            const int4 v = *reinterpret_cast<const int4*>(sc + hi - 3);
+            if (max(max(v.x, v.y), max(v.z, v.w)) >= tau_s) {
+              const int vs[4] = {v.w, v.z, v.y, v.x};   // highest document first
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int dl = hi - u;
-              if (vs[u] >= tau_s && dl < tile_n) {
-                const uint64_t key = make_key_fx(vs[u], uint32_t(doc0 + dl));
-                if (key > tau) {
-                  const int pos = atomicAdd(&s_cnt, 1);
-                  if (pos < cap) mbuf[kk + pos] = key;
+              for (int u = 0; u < 4; ++u) {
+                const int dl = hi - u;
+                if (vs[u] >= tau_s && dl < tile_n) {
+                  const uint64_t key = make_key_fx(vs[u], uint32_t(doc0 + dl));
+                  if (key > tau) {
+                    const int pos = atomicAdd(&s_cnt, 1);
+                    if (pos < cap) mbuf[kk + pos] = key;
+                  }
                 }
               }
             }
           }
-        }
-      };
-      int done = 0;
-      while (done < T) {
-        const bool cold = (s_tau == 0);
-        // Steps grow geometrically with the number of documents this (slice, query) has seen: a step of 3x the
-        // documents seen yields about 3*kk survivors, so every early merge is a small sort.
-        const long long grow = 3 * seen;
-        long long want = grow > BM25_COLD_STEP ? grow : BM25_COLD_STEP;
-        if (want > T - done) want = T - done;
-        const int step = cold ? BM25_COLD_STEP : int(want);
-        const int cnt_before = s_cnt;
-        __syncthreads();
-        scan_range(done, step);
-        __syncthreads();
-        if (s_cnt > cap) {
-          // more survivors than the append area holds (some were dropped): redo the range in segments
-          // that cannot overflow, merging whenever the area fills up
+        };
+        int done = 0;
+        while (done < T) {
+          const bool cold = (s_tau == 0);
+          // Steps grow geometrically with the number of documents this (slice, query) has seen: a step of 3x the
+          // documents seen yields about 3*kk survivors, so every early merge is a small sort.
+          const long long grow = 3 * seen;
+          long long want = grow > BM25_COLD_STEP ? grow : BM25_COLD_STEP;
+          if (want > T - done) want = T - done;
+          const int step = cold ? BM25_COLD_STEP : int(want);
+          const int cnt_before = s_cnt;
           __syncthreads();
-          if (tid == 0) s_cnt = cnt_before;
+          scan_range(done, step);
           __syncthreads();
-          for (int d2 = done; d2 < done + step; d2 += BM25_SEG) {
-            if (s_cnt > cap - BM25_SEG) merge(q);
-            scan_range(d2, min(BM25_SEG, done + step - d2));
+          if (s_cnt > cap) {
+            // more survivors than the append area holds (some were dropped): redo the range in segments
+            // that cannot overflow, merging whenever the area fills up
             __syncthreads();
+            if (tid == 0) s_cnt = cnt_before;
+            __syncthreads();
+            for (int d2 = done; d2 < done + step; d2 += BM25_SEG) {
+              if (s_cnt > cap - BM25_SEG) merge(q);
+              scan_range(d2, min(BM25_SEG, done + step - d2));
+              __syncthreads();
+            }
           }
+          done += step;
+          seen += step;
+          // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a
+          // tighter threshold pays for the sort, as soon as a cold list can be filled, when the append
+          // area is half full, and at the very end of this CTA's tiles.
+          const bool last = (done >= T) && (j == tile_lo);
+          const int cnt = s_cnt;
+          if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk)))
+            merge(q);
         }
-        done += step;
-        seen += step;
-        // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a
-        // tighter threshold pays for the sort, as soon as a cold list can be filled, when the append
-        // area is half full, and at the very end of this CTA's tiles.
-        const bool last = (done >= T) && (j == tile_lo);
-        const int cnt = s_cnt;
-        if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk)))
-          merge(q);
       }
     }
-    for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];
+    if constexpr (EXACT) {
+      for (int i = tid; i < kprime; i += BM25_THREADS) {
+        const Pair64 v = pbuf[i];
+        e_scores[(size_t(blockIdx.x) * q_stride + q) * kprime + i] = v.id < 0 ? -INFINITY : unord64(v.s);
+        e_ids[(size_t(blockIdx.x) * q_stride + q) * kprime + i] = v.id;
+      }
+    } else {
+      for (int i = tid; i < kk; i += BM25_THREADS) parts[(size_t(blockIdx.x) * q_stride + q) * kk + i] = mbuf[i];
+    }
     __syncthreads();
   }
 }
 
-// exact fp64 re-scoring of the candidates; rank_bm25 operation order:
-//   score += idf[t] * ( tf*(k1+1) / ( tf + k1*(1-b+b*dl/avgdl) ) )
+// Exact fp64 re-scoring of the kk candidates (bm25_exact_score), ranking by (score desc, doc desc), and the
+// PROOF that the pre-selection did not lose a member of the true top-k'.
+//   Stored impacts are round(impact * 2^s); the kernel adds (stored >> sh).  For a document d and a query of nt
+//   token occurrences:   exact(d) <= fx(d) * 2^(sh-s) + E,   E = nt * (2^sh - 0.5) * 2^-s   (and >= ... - E).
+//   Let L be the exact k'-th best score among the candidates (a lower bound of the true k'-th best, these are
+//   real documents).  A document can belong to the true top-k' only if exact(d) >= L, i.e. only if
+//   fx(d) >= fx_low := floor((L - E) * 2^(s-sh)) - 1.  Documents outside the candidate list have
+//   (fx, doc) below the list's smallest key; if that key's fx is < fx_low none of them qualifies:
+//   flag 0 = proven.  Otherwise flag 1: the escalation pass re-scores every document with fx >= fx_low.
+//   A list that is not full holds every document: proven.
 __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, const int32_t* __restrict__ q_terms,
                                                            const int32_t* __restrict__ q_offsets,
                                                            const uint64_t* __restrict__ cand, int kk, int kprime,
                                                            double* __restrict__ out_scores,
-                                                           int64_t* __restrict__ out_ids) {
+                                                           int64_t* __restrict__ out_ids, int32_t* __restrict__ flags,
+                                                           int32_t* __restrict__ fx_low, int force_flag) {
   __shared__ uint64_t skey[256];
   __shared__ int64_t sdoc[256];
+  __shared__ double s_kth_score;
+  __shared__ int s_valid;
   const int q = blockIdx.x, c = threadIdx.x;
   const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
   uint64_t okey = 0;
@@ -325,31 +428,13 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
     const uint64_t key = cand[size_t(q) * kk + c];
     if (key != 0) {
       doc = key_row(key);
-      const int j = int(doc / ix.tile_docs);
-      const double kd = ix.d_doc_kd[doc];
-      for (int ti = t0; ti < t1; ++ti) {
-        const int t = q_terms[ti];
-        if (t < 0 || t >= ix.n_terms) continue;
-        const int64_t base = ix.d_term_offsets[t];
-        const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
-        int64_t lo = base + tp[0], hi = base + tp[1];  // [lo, hi)
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (ix.d_post_doc[mid] < uint32_t(doc)) lo = mid + 1;
-          else hi = mid;
-        }
-        if (lo < base + tp[1] && ix.d_post_doc[lo] == uint32_t(doc)) {
-          const double tf = double(ix.d_post_tf[lo]);
-          const double num = __dmul_rn(tf, ix.k1_plus_1);
-          const double den = __dadd_rn(tf, kd);
-          score = __dadd_rn(score, __dmul_rn(ix.d_idf[t], __ddiv_rn(num, den)));
-        }
-      }
+      score = bm25_exact_score(ix, q_terms, t0, t1, doc);
       okey = ord64(score);
     }
   }
   skey[c] = okey;
   sdoc[c] = doc;
+  if (c == 0) s_valid = 0;
   __syncthreads();
   if (c < kk && doc >= 0) {
     int rank = 0;
@@ -363,16 +448,28 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
       out_scores[size_t(q) * kprime + rank] = score;
       out_ids[size_t(q) * kprime + rank] = doc;
     }
+    if (rank == kprime - 1) s_kth_score = score;
+    atomicAdd(&s_valid, 1);
   }
+  __syncthreads();
   // pad the tail when fewer than k' candidates exist
-  __shared__ int s_valid;
-  if (c == 0) s_valid = 0;
-  __syncthreads();
-  if (c < kk && doc >= 0) atomicAdd(&s_valid, 1);
-  __syncthreads();
   for (int i = s_valid + c; i < kprime; i += blockDim.x) {
     out_scores[size_t(q) * kprime + i] = -INFINITY;
     out_ids[size_t(q) * kprime + i] = -1;
+  }
+  if (c == 0 && flags != nullptr) {
+    int flag = 0, fl = INT_MIN;
+    const uint64_t kmin = cand[size_t(q) * kk + kk - 1];   // the merged list is sorted: non-zero <=> full
+    if (kmin != 0) {
+      const int nt = t1 - t0, sh = bm25_query_shift(nt), s = ix.impact_scale_log2;
+      const double E = double(nt) * (ldexp(1.0, sh) - 0.5 + 1e-6) * ldexp(1.0, -s);
+      const double L = s_kth_score;
+      const double thr = ldexp(L - E - fabs(L) * 1e-12, s - sh);
+      fl = thr <= -2147483000.0 ? INT_MIN : (thr >= 2147483000.0 ? INT_MAX : int(floor(thr)) - 1);
+      flag = key_fx(kmin) < fl ? 0 : 1;
+    }
+    flags[q] = force_flag ? 1 : flag;
+    fx_low[q] = fl;
   }
 }
 
@@ -401,29 +498,50 @@ static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& gy,
 
 using namespace drs;
 
+// workspace layout (bytes): parts | cand | gtau | merge scratch | flags | fx_low | e_scores | e_ids
+struct Bm25Ws {
+  size_t parts, cand, gtau, mscratch, flags, fxlow, escores, eids, total;
+};
+static Bm25Ws bm25_ws(int n_queries, int gx, int kk, int kprime) {
+  Bm25Ws w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = o;
+    o += (bytes + 255) & ~size_t(255);
+    return at;
+  };
+  w.parts = take(size_t(gx) * n_queries * kk * 8);
+  w.cand = take(size_t(n_queries) * kk * 8);
+  w.gtau = take(size_t(n_queries) * 8);
+  w.mscratch = take(merge_scratch_keys(gx, n_queries, kk) * 8);
+  w.flags = take(size_t(n_queries) * 4);
+  w.fxlow = take(size_t(n_queries) * 4);
+  w.escores = take(size_t(gx) * n_queries * kprime * 8);
+  w.eids = take(size_t(gx) * n_queries * kprime * 8);
+  w.total = o + 256;
+  return w;
+}
+
 extern "C" size_t drs_bm25_workspace_bytes(int n_queries, const drs_bm25_index* index, int kprime) {
   if (!index || n_queries < 0 || kprime <= 0) return 0;
   int gx, gy, tpc;
   bm25_grid(index, n_queries > 0 ? n_queries : 1, gx, gy, tpc);
-  const size_t kk = cand_len(kprime);
-  size_t b = size_t(gx) * n_queries * kk * 8;  // partial lists
-  b += size_t(n_queries) * kk * 8;             // merged candidates
-  b += size_t(n_queries) * 8;                  // shared thresholds
-  b += merge_scratch_keys(gx, n_queries, int(kk)) * 8;  // two-level merge scratch
-  return b + 256;
+  return bm25_ws(n_queries, gx, cand_len(kprime), kprime).total;
 }
 
-extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
-                             int n_queries, int kprime, double* d_out_scores, int64_t* d_out_ids,
-                             void* d_workspace, size_t workspace_bytes, void* stream) {
+extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
+                                int n_queries, int kprime, int mode, double* d_out_scores, int64_t* d_out_ids,
+                                int32_t* d_out_flags, void* d_workspace, size_t workspace_bytes, void* stream) {
   DRS_REQUIRE(index && d_q_offsets && d_out_scores && d_out_ids && d_workspace, DRS_ERR_ARG, "bm25: null pointer");
   DRS_REQUIRE(n_queries >= 0 && kprime > 0, DRS_ERR_ARG, "bm25: bad sizes");
+  DRS_REQUIRE(mode >= 0 && mode <= 2, DRS_ERR_ARG, "bm25: mode must be 0 (auto), 1 (no escalation) or 2 (escalate all)");
   DRS_REQUIRE(kprime <= DRS_MAX_KPRIME, DRS_ERR_UNSUPPORTED, "bm25: k' exceeds DRS_MAX_KPRIME");
   const drs_bm25_index& ix = *index;
   DRS_REQUIRE(ix.n_docs > 0 && ix.n_docs < (int64_t(1) << 32), DRS_ERR_UNSUPPORTED, "bm25: n_docs out of range");
   DRS_REQUIRE(ix.tile_docs >= 256 && ix.tile_docs <= 8192 && (ix.tile_docs & (ix.tile_docs - 1)) == 0,
               DRS_ERR_UNSUPPORTED, "bm25: tile_docs must be a power of two in [256, 8192]");
   DRS_REQUIRE(ix.n_tiles == int((ix.n_docs + ix.tile_docs - 1) / ix.tile_docs), DRS_ERR_ARG, "bm25: n_tiles mismatch");
+  DRS_REQUIRE(ix.impact_scale_log2 >= -64 && ix.impact_scale_log2 <= 64, DRS_ERR_ARG, "bm25: impact_scale_log2 out of range");
   DRS_REQUIRE(workspace_bytes >= drs_bm25_workspace_bytes(n_queries, index, kprime), DRS_ERR_WORKSPACE,
               "bm25: workspace too small");
   if (n_queries == 0) return DRS_OK;
@@ -431,26 +549,50 @@ extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_ter
   const int kk = cand_len(kprime);
   int gx, gy, tpc;
   bm25_grid(index, n_queries, gx, gy, tpc);
-  uint64_t* parts = reinterpret_cast<uint64_t*>(d_workspace);
-  uint64_t* cand = parts + size_t(gx) * n_queries * kk;
-  unsigned long long* gtau = reinterpret_cast<unsigned long long*>(cand + size_t(n_queries) * kk);
+  const Bm25Ws w = bm25_ws(n_queries, gx, kk, kprime);
+  uint8_t* base = reinterpret_cast<uint8_t*>(d_workspace);
+  uint64_t* parts = reinterpret_cast<uint64_t*>(base + w.parts);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(base + w.cand);
+  unsigned long long* gtau = reinterpret_cast<unsigned long long*>(base + w.gtau);
+  uint64_t* mscratch = merge_scratch_keys(gx, n_queries, kk) ? reinterpret_cast<uint64_t*>(base + w.mscratch) : nullptr;
+  int32_t* flags = reinterpret_cast<int32_t*>(base + w.flags);
+  int32_t* fxlow = reinterpret_cast<int32_t*>(base + w.fxlow);
+  double* escores = reinterpret_cast<double*>(base + w.escores);
+  int64_t* eids = reinterpret_cast<int64_t*>(base + w.eids);
   DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8, st));
   const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
-  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
-    bm25_select_kernel<<<dim3(gx, gy), BM25_THREADS, smem, st>>>(ix, d_q_terms, d_q_offsets, n_queries, kk, tpc,
-                                                                 parts, n_queries, gtau);
+    bm25_select_kernel<false><<<dim3(gx, gy), BM25_THREADS, smem, st>>>(
+        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr);
     count_launches(1);
   }
   DRS_CUDA_CHECK(cudaGetLastError());
   ProfScope pt(DRS_PROF_BM25_TAIL, st);
-  uint64_t* mscratch = merge_scratch_keys(gx, n_queries, kk) ? reinterpret_cast<uint64_t*>(gtau + n_queries) : nullptr;
   int rc = launch_merge_keys(parts, gx, n_queries, n_queries, kk, cand, nullptr, mscratch, st);
   if (rc != DRS_OK) return rc;
-  bm25_rescore_kernel<<<n_queries, 256, 0, st>>>(ix, d_q_terms, d_q_offsets, cand, kk, kprime, d_out_scores,
-                                                 d_out_ids);
+  bm25_rescore_kernel<<<n_queries, 256, 0, st>>>(ix, d_q_terms, d_q_offsets, cand, kk, kprime, d_out_scores, d_out_ids,
+                                                 flags, fxlow, mode == 2 ? 1 : 0);
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
+  if (mode != 1) {
+    // escalation, predicated on the device-side flags (no host round trip): CTAs of proven queries exit at once
+    bm25_select_kernel<true><<<dim3(gx, gy), BM25_THREADS, smem, st>>>(
+        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids);
+    count_launches(1);
+    DRS_CUDA_CHECK(cudaGetLastError());
+    rc = launch_merge_pairs_f64(escores, eids, gx, n_queries, kprime, kprime, d_out_scores, d_out_ids, flags, st);
+    if (rc != DRS_OK) return rc;
+  }
+  if (d_out_flags) DRS_CUDA_CHECK(cudaMemcpyAsync(d_out_flags, flags, size_t(n_queries) * 4, cudaMemcpyDeviceToDevice, st));
   return DRS_OK;
+}
+
+extern "C" int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
+                             int n_queries, int kprime, double* d_out_scores, int64_t* d_out_ids,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+  return drs_bm25_topk_ex(index, d_q_terms, d_q_offsets, n_queries, kprime, 0, d_out_scores, d_out_ids, nullptr,
+                          d_workspace, workspace_bytes, stream);
 }

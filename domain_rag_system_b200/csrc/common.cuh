@@ -83,6 +83,20 @@ __device__ __forceinline__ uint64_t ord64(double d) {
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
+__device__ __forceinline__ double unord64(uint64_t k) {
+  const uint64_t u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)u);
+}
+
+// (score, id) pair ordered by (score, id); s is the ordered image of the score, id -1 = absent
+struct Pair64 {
+  uint64_t s;
+  int64_t id;
+};
+__device__ __forceinline__ bool pair_less(const Pair64& a, const Pair64& b) {
+  return (a.s < b.s) || (a.s == b.s && a.id < b.id);
+}
+
 // ---- block-wide bitonic sort, descending, n a power of two, data in shared memory -------
 template <typename T, typename Less>
 __device__ __forceinline__ void block_bitonic_desc(T* s, int n, Less less) {
@@ -136,6 +150,8 @@ int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, 
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
                          const int32_t* d_active, int query_mode, int flag_unproven, int flag_proven,
                          cudaStream_t st);
+int launch_merge_pairs_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries, int k, int k_out,
+                           double* d_out_scores, int64_t* d_out_ids, int32_t* d_flags, cudaStream_t st);
 // dense_simt.cu
 int dense_simt_grid();
 int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,

@@ -214,23 +214,18 @@ int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, 
 // ------------------------------------------------------------------------------------------
 // C-ABI merges (post all-gather).  (score, id) pairs, order (score desc, id desc).
 // ------------------------------------------------------------------------------------------
-struct Pair64 {
-  uint64_t s;  // ordered image of the score
-  int64_t id;  // -1 = absent
-};
-__device__ __forceinline__ bool pair_less(const Pair64& a, const Pair64& b) {
-  return (a.s < b.s) || (a.s == b.s && a.id < b.id);
-}
-
+// flags (optional): only queries with flags[q] == 1 are merged; their flag becomes 2 afterwards (the BM25
+// escalation pass: "resolved exactly").
 template <typename ScoreT>
 __global__ void __launch_bounds__(256) merge_pairs_kernel(const ScoreT* __restrict__ scores,
                                                           const int64_t* __restrict__ ids, int n_parts,
                                                           int n_queries, int k, int k_out,
                                                           ScoreT* __restrict__ out_scores,
-                                                          int64_t* __restrict__ out_ids) {
+                                                          int64_t* __restrict__ out_ids, int32_t* __restrict__ flags) {
   constexpr int BUF = 1024;
   __shared__ Pair64 buf[BUF];
   const int q = blockIdx.x;
+  if (flags != nullptr && flags[q] != 1) return;
   const int n = n_parts * k;
   for (int i = threadIdx.x; i < k_out; i += blockDim.x) buf[i] = Pair64{0, -1};
   int pos = 0;
@@ -262,27 +257,31 @@ __global__ void __launch_bounds__(256) merge_pairs_kernel(const ScoreT* __restri
     ScoreT s;
     if (v.id < 0) s = ScoreT(-INFINITY);
     else if constexpr (sizeof(ScoreT) == 4) s = ScoreT(unord32(uint32_t(v.s >> 32)));
-    else {
-      const uint64_t u = (v.s >> 63) ? (v.s & 0x7fffffffffffffffull) : ~v.s;
-      s = ScoreT(__longlong_as_double((long long)u));
-    }
+    else s = ScoreT(unord64(v.s));
     out_scores[size_t(q) * k_out + i] = s;
     out_ids[size_t(q) * k_out + i] = v.id;
   }
+  __syncthreads();
+  if (flags != nullptr && threadIdx.x == 0) flags[q] = 2;
 }
 
 template <typename ScoreT>
 static int merge_pairs(const ScoreT* d_scores, const int64_t* d_ids, int n_parts, int n_queries, int k,
-                       int k_out, ScoreT* d_out_scores, int64_t* d_out_ids, void* stream) {
+                       int k_out, ScoreT* d_out_scores, int64_t* d_out_ids, void* stream, int32_t* d_flags = nullptr) {
   DRS_REQUIRE(d_scores && d_ids && d_out_scores && d_out_ids, DRS_ERR_ARG, "merge: null pointer");
   DRS_REQUIRE(n_parts > 0 && n_queries >= 0 && k > 0 && k_out > 0, DRS_ERR_ARG, "merge: bad sizes");
   DRS_REQUIRE(k_out <= 512, DRS_ERR_UNSUPPORTED, "merge: k_out > 512");
   if (n_queries == 0) return DRS_OK;
   merge_pairs_kernel<ScoreT><<<n_queries, 256, 0, (cudaStream_t)stream>>>(
-      d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids);
+      d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids, d_flags);
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
+}
+
+int launch_merge_pairs_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries, int k, int k_out,
+                           double* d_out_scores, int64_t* d_out_ids, int32_t* d_flags, cudaStream_t st) {
+  return merge_pairs<double>(d_scores, d_ids, n_parts, n_queries, k, k_out, d_out_scores, d_out_ids, (void*)st, d_flags);
 }
 
 }  // namespace drs

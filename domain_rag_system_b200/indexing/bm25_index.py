@@ -241,7 +241,7 @@ class Bm25DeviceIndex:
     def struct(self) -> _lib.Bm25IndexStruct:
         if self._struct is None:
             s = _lib.Bm25IndexStruct()
-            s.n_docs, s.n_terms, s.tile_docs, s.n_tiles, s.reserved = (self.n_docs, self.n_terms, self.tile_docs,
+            s.n_docs, s.n_terms, s.tile_docs, s.n_tiles, s.impact_scale_log2 = (self.n_docs, self.n_terms, self.tile_docs,
                                                                        self.n_tiles, self.impact_scale_log2)
             t = self.t
             s.d_term_offsets = t["term_offsets"].data_ptr()

@@ -130,6 +130,18 @@ size_t drs_bm25_workspace_bytes(int n_queries, const drs_bm25_index* index, int 
 int drs_bm25_topk(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
                   int n_queries, int kprime, double* d_out_scores, int64_t* d_out_ids,
                   void* d_workspace, size_t workspace_bytes, void* stream);
+/* Same call with the exactness machinery exposed (same reference lines).  Documents are pre-selected on
+ * integer (fixed-point) scores, the k'+margin survivors are re-scored in fp64, and an error bound then
+ * PROVES that no other document can belong to the top-k'; queries it cannot prove (large groups of
+ * near-ties around the k'-th score) are escalated on the device: every document that can still qualify
+ * is re-scored exactly.
+ *   mode          0 = prove, escalate the unproven (what drs_bm25_topk does);
+ *                 1 = prove only (diagnostics: flag 1 marks unproven queries);
+ *                 2 = escalate every query (test hook for the escalation pass)
+ *   d_out_flags   [Q] int32 or NULL: 0 proven, 1 unproven (mode 1 only), 2 resolved by escalation   */
+int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_terms, const int32_t* d_q_offsets,
+                     int n_queries, int kprime, int mode, double* d_out_scores, int64_t* d_out_ids,
+                     int32_t* d_out_flags, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * Score fusion + final top-K.

@@ -86,6 +86,8 @@ def test_host_index_build_matches_oracle(n, vocab):
     fx = ix.t["post_impact"].numpy()[:nnz].astype(np.int64)
     assert np.abs(fx).max() <= 2 ** 26 and np.abs(orc.idf).max() * 2.5 * 2.0 ** (s + 1) > 2 ** 26
     assert np.abs(fx - imp * 2.0 ** s).max() <= 0.5
+    st = ix.struct()   # the C struct carries the scale (the kernel's exactness bound is computed from it)
+    assert st.impact_scale_log2 == s and st.n_docs == n and st.n_tiles == ix.n_tiles
 
 
 def test_string_corpus_build_assigns_ids_in_first_appearance_order():

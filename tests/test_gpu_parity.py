@@ -142,21 +142,41 @@ def test_dense_umma_mask_and_auto_dispatch():
 # BM25
 # ----------------------------------------------------------------------------------------------
 def _check_bm25(offs, toks, vocab, queries, kprime, k1=1.5, b=0.75, tile_docs=None, dense_frac=0.25):
+    """Every mode of drs_bm25_topk_ex against the oracle: "auto" and "escalate_all" must be exact for every
+    query; with "no_escalation" every query the error bound PROVES (flag 0) must be exact."""
     ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, k1=k1, b=b, device=DEV, tile_docs=tile_docs,
                                         dense_frac=dense_frac)
     orc = obm25.Bm25Csr(offs, toks, vocab, k1=k1, b=b)
     qt, qo = ix.encode_queries(queries)
-    sc, ids = _lib.bm25_topk(ix.struct(), qt.to(DEV), qo.to(DEV), len(queries), kprime)
-    torch.cuda.synchronize()
-    sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
     n = len(offs) - 1
-    for i, q in enumerate(queries):
+    want = []
+    for q in queries:
         full = orc.get_scores(q)
         order = obm25.stable_desc_order(full)[:kprime]
+        want.append((order, full[order]))
+    stats = {}
+    for mode in ("auto", "escalate_all", "no_escalation"):
+        sc, ids, flags = _lib.bm25_topk(ix.struct(), qt.to(DEV), qo.to(DEV), len(queries), kprime, mode=mode,
+                                        want_flags=True)
+        torch.cuda.synchronize()
+        sc, ids, flags = sc.cpu().numpy(), ids.cpu().numpy(), flags.cpu().numpy()
+        stats[mode] = flags
+        if mode == "escalate_all":
+            assert (flags == 2).all()
+        elif mode == "auto":
+            assert np.isin(flags, (0, 2)).all()
+        else:
+            assert np.isin(flags, (0, 1)).all()
         k_eff = min(kprime, n)
-        assert np.array_equal(ids[i][:k_eff], order[:k_eff]), f"bm25 q{i}: ids differ"
-        assert np.array_equal(sc[i][:k_eff], full[order[:k_eff]]), f"bm25 q{i}: scores not bit-identical"
-        assert (ids[i][k_eff:] == -1).all()
+        for i in range(len(queries)):
+            if mode == "no_escalation" and flags[i] == 1:
+                continue
+            order, scores = want[i]
+            assert np.array_equal(ids[i][:k_eff], order[:k_eff]), f"bm25 {mode} q{i}: ids differ"
+            assert np.array_equal(sc[i][:k_eff], scores[:k_eff]), f"bm25 {mode} q{i}: scores not bit-identical"
+            assert (ids[i][k_eff:] == -1).all()
+    assert np.array_equal(stats["auto"] == 2, stats["no_escalation"] == 1)
+    return stats["auto"]
 
 
 @pytest.mark.parametrize("kprime", [1, 10, 60, 100, 128])
@@ -173,7 +193,9 @@ def test_bm25_shapes(n, vocab, tile):
     qs = synth.zipf_queries(40, offs, toks, vocab=vocab, seed=n + 1)
     qs += [np.array([], dtype=np.int32), np.array([-1, -1], dtype=np.int32),             # empty / all-OOV
            np.array([vocab - 1] * 5, dtype=np.int32), np.array([0, 0, 1, 0], dtype=np.int32)]  # rare / repeated head terms
-    _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile)
+    flags = _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile)
+    if n >= 20000 and vocab >= 5000:   # ordinary Zipfian queries on a real-sized corpus are proven, not escalated
+        assert (flags[:40] == 0).mean() >= 0.9, flags
     _check_bm25(offs, toks, vocab, qs[:6], 20, k1=1.2, b=0.3, tile_docs=tile)
     _check_bm25(offs, toks, vocab, qs, 20, tile_docs=tile, dense_frac=0.0)     # postings-only path
 
@@ -423,3 +445,20 @@ def test_bm25_adversarial_monotone_scores_overflow_path():
     queries = [np.array([0], dtype=np.int32), np.array([0, 1, 0], dtype=np.int32), np.array([1], dtype=np.int32)]
     _check_bm25(offs, toks, 3, queries, 20, tile_docs=8192, dense_frac=0.0)
     _check_bm25(offs, toks, 3, queries, 20, tile_docs=8192)
+
+
+def test_bm25_long_queries_shifted_impacts_and_mass_ties():
+    """Queries of more than 16 token occurrences shift the fixed-point impacts (and more than 64 restage the
+    term metadata per tile); a corpus of duplicated documents puts hundreds of exact ties around the k'-th
+    score, which the error bound cannot prove => the escalation pass must resolve them (larger id first)."""
+    rng = np.random.default_rng(12)
+    base_offs, base_toks = synth.zipf_docs(500, vocab=300, seed=4, len_min=5, len_max=30)
+    reps = 24                                     # every document 24 times
+    docs = [base_toks[base_offs[i]:base_offs[i + 1]] for i in range(500)] * reps
+    offs = np.zeros(len(docs) + 1, dtype=np.int64)
+    np.cumsum([len(d) for d in docs], out=offs[1:])
+    toks = np.concatenate(docs).astype(np.int32)
+    queries = [rng.integers(0, 300, size=m).astype(np.int32) for m in (17, 33, 64, 65, 150, 300)]
+    queries += [np.array([5, 9, 11], dtype=np.int32)]
+    flags = _check_bm25(offs, toks, 300, queries, 10, tile_docs=1024)
+    assert (flags == 2).any()                     # 24-fold ties straddle the candidate margin
