@@ -204,35 +204,56 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           tp1 = __ldg(tp + 1);
         }
         const int nd = s_nd;
-        // -- pass A: dense rows, up to four fused per sweep; the first sweep also initialises the tile
+        // -- pass A: dense rows (packed 14-bit values, 8 documents per 16-byte load), up to four rows summed as
+        // packed 16-bit lanes per sweep; the first sweep also initialises the tile.  16-byte group i of a row
+        // holds documents 4i..4i+3 of the tile's first half and 4i..4i+3 of its second half, so a thread's two
+        // shared-memory accesses (int4 i and int4 T/8 + i) are conflict free.
         int4* dst = reinterpret_cast<int4*>(sc);
+        const int T8 = T >> 3;
+        const int dk = ix.dense_shift - sh;   // row value -> score units: << dk (>> -dk when negative)
+        auto unpack_add = [&](int4& lo4, int4& hi4, const uint4 w) {
+          if (dk >= 0) {
+            lo4.x += int((w.x & 0xffffu) << dk); lo4.y += int((w.x >> 16) << dk);
+            lo4.z += int((w.y & 0xffffu) << dk); lo4.w += int((w.y >> 16) << dk);
+            hi4.x += int((w.z & 0xffffu) << dk); hi4.y += int((w.z >> 16) << dk);
+            hi4.z += int((w.w & 0xffffu) << dk); hi4.w += int((w.w >> 16) << dk);
+          } else {
+            lo4.x += int((w.x & 0xffffu) >> -dk); lo4.y += int((w.x >> 16) >> -dk);
+            lo4.z += int((w.y & 0xffffu) >> -dk); lo4.w += int((w.y >> 16) >> -dk);
+            hi4.x += int((w.z & 0xffffu) >> -dk); hi4.y += int((w.z >> 16) >> -dk);
+            hi4.z += int((w.w & 0xffffu) >> -dk); hi4.w += int((w.w >> 16) >> -dk);
+          }
+        };
         for (int g0 = 0; g0 < nd; g0 += 4) {
           const int ng = min(4, nd - g0);
-          const int4* r0 = reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
-          const int4* r1 = ng > 1 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
-          const int4* r2 = ng > 2 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
-          const int4* r3 = ng > 3 ? reinterpret_cast<const int4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
+          const uint4* r0 = reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
+          const uint4* r1 = ng > 1 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
+          const uint4* r2 = ng > 2 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
+          const uint4* r3 = ng > 3 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
+          const uint4 zu = make_uint4(0, 0, 0, 0);
           const int4 z = make_int4(0, 0, 0, 0);
-          for (int i = tid; i < T / 4; i += 2 * BM25_THREADS) {
+          for (int i = tid; i < T8; i += 2 * BM25_THREADS) {
             const int i2 = i + BM25_THREADS;
-            const bool two = i2 < T / 4;
-            const int4 a0 = __ldg(r0 + i), a1 = ng > 1 ? __ldg(r1 + i) : z, a2 = ng > 2 ? __ldg(r2 + i) : z,
-                       a3 = ng > 3 ? __ldg(r3 + i) : z;
-            const int4 b0 = two ? __ldg(r0 + i2) : z, b1 = (two && ng > 1) ? __ldg(r1 + i2) : z,
-                       b2 = (two && ng > 2) ? __ldg(r2 + i2) : z, b3 = (two && ng > 3) ? __ldg(r3 + i2) : z;
-            int4 x = tile_init ? dst[i] : z;
-            x.x += (a0.x >> sh) + (a1.x >> sh) + (a2.x >> sh) + (a3.x >> sh);
-            x.y += (a0.y >> sh) + (a1.y >> sh) + (a2.y >> sh) + (a3.y >> sh);
-            x.z += (a0.z >> sh) + (a1.z >> sh) + (a2.z >> sh) + (a3.z >> sh);
-            x.w += (a0.w >> sh) + (a1.w >> sh) + (a2.w >> sh) + (a3.w >> sh);
-            dst[i] = x;
+            const bool two = i2 < T8;
+            const uint4 a0 = __ldg(r0 + i), a1 = ng > 1 ? __ldg(r1 + i) : zu, a2 = ng > 2 ? __ldg(r2 + i) : zu,
+                        a3 = ng > 3 ? __ldg(r3 + i) : zu;
+            const uint4 b0 = two ? __ldg(r0 + i2) : zu, b1 = (two && ng > 1) ? __ldg(r1 + i2) : zu,
+                        b2 = (two && ng > 2) ? __ldg(r2 + i2) : zu, b3 = (two && ng > 3) ? __ldg(r3 + i2) : zu;
+            {
+              const uint4 w = make_uint4(a0.x + a1.x + a2.x + a3.x, a0.y + a1.y + a2.y + a3.y,
+                                         a0.z + a1.z + a2.z + a3.z, a0.w + a1.w + a2.w + a3.w);
+              int4 lo4 = tile_init ? dst[i] : z, hi4 = tile_init ? dst[T8 + i] : z;
+              unpack_add(lo4, hi4, w);
+              dst[i] = lo4;
+              dst[T8 + i] = hi4;
+            }
             if (two) {
-              int4 y = tile_init ? dst[i2] : z;
-              y.x += (b0.x >> sh) + (b1.x >> sh) + (b2.x >> sh) + (b3.x >> sh);
-              y.y += (b0.y >> sh) + (b1.y >> sh) + (b2.y >> sh) + (b3.y >> sh);
-              y.z += (b0.z >> sh) + (b1.z >> sh) + (b2.z >> sh) + (b3.z >> sh);
-              y.w += (b0.w >> sh) + (b1.w >> sh) + (b2.w >> sh) + (b3.w >> sh);
-              dst[i2] = y;
+              const uint4 w = make_uint4(b0.x + b1.x + b2.x + b3.x, b0.y + b1.y + b2.y + b3.y,
+                                         b0.z + b1.z + b2.z + b3.z, b0.w + b1.w + b2.w + b3.w);
+              int4 lo4 = tile_init ? dst[i2] : z, hi4 = tile_init ? dst[T8 + i2] : z;
+              unpack_add(lo4, hi4, w);
+              dst[i2] = lo4;
+              dst[T8 + i2] = hi4;
             }
           }
           tile_init = true;   // the same thread owns the same documents in every sweep: no barrier between sweeps
@@ -401,8 +422,9 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
 
 // Exact fp64 re-scoring of the kk candidates (bm25_exact_score), ranking by (score desc, doc desc), and the
 // PROOF that the pre-selection did not lose a member of the true top-k'.
-//   Stored impacts are round(impact * 2^s); the kernel adds (stored >> sh).  For a document d and a query of nt
-//   token occurrences:   exact(d) <= fx(d) * 2^(sh-s) + E,   E = nt * (2^sh - 0.5) * 2^-s   (and >= ... - E).
+//   Stored impacts are round(impact * 2^s); the kernel adds (stored >> sh) for postings terms and the coarser
+//   dense-row value for head terms.  For a document d and a query of nt token occurrences:
+//   exact(d) <= fx(d) * 2^(sh-s) + E,   E = sum over the tokens of their rounding + shift error (below).
 //   Let L be the exact k'-th best score among the candidates (a lower bound of the true k'-th best, these are
 //   real documents).  A document can belong to the true top-k' only if exact(d) >= L, i.e. only if
 //   fx(d) >= fx_low := floor((L - E) * 2^(s-sh)) - 1.  Documents outside the candidate list have
@@ -462,7 +484,16 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
     const uint64_t kmin = cand[size_t(q) * kk + kk - 1];   // the merged list is sorted: non-zero <=> full
     if (kmin != 0) {
       const int nt = t1 - t0, sh = bm25_query_shift(nt), s = ix.impact_scale_log2;
-      const double E = double(nt) * (ldexp(1.0, sh) - 0.5 + 1e-6) * ldexp(1.0, -s);
+      // per token occurrence, in units of 2^-s: a postings term is off by < 2^sh - 0.5 (rounding when stored +
+      // the floor of the shift); a head term by its row rounding 2^(dense_shift-1) plus a floor of < 2^sh
+      double units = 0.0;
+      for (int ti = t0; ti < t1; ++ti) {
+        const int t = q_terms[ti];
+        if (t < 0 || t >= ix.n_terms) continue;
+        const bool dense = ix.d_dense_slot != nullptr && ix.d_dense_slot[t] >= 0;
+        units += ldexp(1.0, sh) + (dense ? (ix.dense_shift > 0 ? ldexp(1.0, ix.dense_shift - 1) : 0.0) : -0.5) + 1e-6;
+      }
+      const double E = units * ldexp(1.0, -s);
       const double L = s_kth_score;
       const double thr = ldexp(L - E - fabs(L) * 1e-12, s - sh);
       fl = thr <= -2147483000.0 ? INT_MIN : (thr >= 2147483000.0 ? INT_MAX : int(floor(thr)) - 1);

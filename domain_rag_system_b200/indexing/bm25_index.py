@@ -27,6 +27,7 @@ import torch
 from .. import _lib
 
 IMPACT_BITS = 26   # |stored impact| <= 2^26: 16 query tokens sum without a shift (csrc/bm25.cu)
+DENSE_MAX = (1 << 14) - 1   # dense row values are 14-bit unsigned (see include/drs_b200.h)
 POST_PAD = 4       # zeroed entries after the last posting (aligned 4-wide reads)
 
 
@@ -62,6 +63,7 @@ class Bm25DeviceIndex:
         self.total_tokens = 0
         self.n_dense = 0                           # head terms that also have a dense impact row
         self.impact_scale_log2 = 0                 # stored impacts = round(impact * 2^s)
+        self.dense_shift = 0                       # dense row value = round(stored impact / 2^dense_shift)
         self.t: Dict[str, torch.Tensor] = {}       # device tensors
         self._struct = None
 
@@ -188,13 +190,29 @@ class Bm25DeviceIndex:
         heavy = torch.nonzero(df >= max(1.0, dense_frac * n)).flatten()
         if heavy.numel() > max_dense_terms:
             heavy = heavy[torch.argsort(df[heavy], descending=True)[:max_dense_terms]]
-        dense_impact = torch.zeros(max(int(heavy.numel()), 1), n_pad, dtype=torch.int32, device=build_device)
+        dense_impact = torch.zeros(max(int(heavy.numel()), 1), n_pad, dtype=torch.int16, device=build_device)
+        self.dense_shift = 0
         if heavy.numel() and dense_frac > 0:
             dense_slot[heavy] = torch.arange(heavy.numel(), dtype=torch.int32, device=build_device)
             slot_of_post = dense_slot[post_term]
             sel = slot_of_post >= 0
-            dense_impact[slot_of_post[sel].long(), post_doc[sel]] = impact[sel]
-            del slot_of_post, sel
+            imp_d = impact[sel].to(torch.int64)
+            if int(imp_d.min()) < 0:
+                # packed 16-bit lanes are unsigned: a corpus whose head terms carry NEGATIVE impacts (the
+                # epsilon floor of a negative average idf) keeps every term on the postings path
+                dense_slot.fill_(-1)
+            else:
+                # 14-bit row values: four rows add up inside a 16-bit lane without a carry
+                mx = int(imp_d.max())
+                while ((mx + ((1 << self.dense_shift) >> 1)) >> self.dense_shift) > DENSE_MAX:
+                    self.dense_shift += 1
+                v14 = (imp_d + ((1 << self.dense_shift) >> 1)) >> self.dense_shift
+                dense_impact[slot_of_post[sel].long(), post_doc[sel]] = v14.to(torch.int16)
+                # per tile: group i = documents 4i..4i+3 of the first half, then 4i..4i+3 of the second half
+                t8 = self.tile_docs // 8
+                dense_impact = (dense_impact.view(-1, self.n_tiles, 2, t8, 4).permute(0, 1, 3, 2, 4).contiguous()
+                                .view(-1, n_pad))
+            del slot_of_post, sel, imp_d
         else:
             dense_slot.fill_(-1)
         self.n_dense = int((dense_slot >= 0).sum())
@@ -255,6 +273,7 @@ class Bm25DeviceIndex:
             s.d_dense_slot = t["dense_slot"].data_ptr()
             s.d_dense_impact = t["dense_impact"].data_ptr()
             s.dense_stride = self.n_tiles * self.tile_docs
+            s.dense_shift = self.dense_shift
             self._struct = s
         return self._struct
 
@@ -299,6 +318,7 @@ class Bm25DeviceIndex:
                              average_idf=self.average_idf, vocab_present=self.vocab_present,
                              total_tokens=self.total_tokens, row_offset=self.row_offset,
                              impact_scale_log2=self.impact_scale_log2, n_dense=self.n_dense,
+                             dense_shift=self.dense_shift,
                              n_docs_global=self.n_docs_global),
                 "vocab": self.vocab, "tensors": {k: v.cpu() for k, v in self.t.items()}}
 

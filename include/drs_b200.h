@@ -104,14 +104,20 @@ typedef struct drs_bm25_index {
   const double* d_doc_kd;       /* [N] k1*(1-b+b*doc_len/avgdl), fp64, reference op order */
   double k1_plus_1;             /* k1 + 1                                                */
   /* Head terms (present in a large fraction of the documents) additionally carry a DENSE row of
-     per-document impacts: adding a row is a vector add (4 bytes/document, no scatter).  The
-     values are the same fixed-point impacts, 0 where the term is absent, so scores are unchanged.
-     Pre-selection scores are INTEGER sums of these impacts: integer addition is associative, so a
-     document's pre-selection score does not depend on the order its terms are visited in and
-     documents with the same (term, impact) multiset tie exactly, as they do in the reference.  */
+     per-document impacts: adding a row is a vector add (2 bytes/document, no scatter).  Row values are
+     14-bit unsigned: round(stored_impact / 2^dense_shift), 0 where the term is absent -- four rows can be
+     summed as packed 16-bit lanes without a carry.  Pre-selection scores are INTEGER sums of impacts:
+     integer addition is associative, so a document's pre-selection score does not depend on the order
+     its terms are visited in and documents with the same (term, impact) multiset tie exactly, as they
+     do in the reference.  A head term is ALWAYS added from its row, so the coarser rounding of the rows
+     keeps that property; it only widens the error bound of the exactness proof.
+     Layout of a row: per tile, 16-byte group i (i < tile_docs/8) holds the four documents 4i..4i+3 of the
+     tile's first half followed by the four documents 4i..4i+3 of its second half.                   */
   const int32_t* d_dense_slot;  /* [V] row of the term in d_dense_impact, -1 = sparse only; may be NULL */
-  const int32_t* d_dense_impact;/* [n_dense, dense_stride] fixed point, same scale       */
+  const uint16_t* d_dense_impact;/* [n_dense, dense_stride]                              */
   int64_t dense_stride;         /* n_tiles * tile_docs (rows are zero padded)            */
+  int32_t dense_shift;          /* row value * 2^dense_shift ~ stored impact             */
+  int32_t reserved;
 } drs_bm25_index;
 
 /* ---------------------------------------------------------------------------------

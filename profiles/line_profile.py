@@ -3,8 +3,9 @@
 instructions executed) with the line table nvdisasm prints for the SAME build of libdrs_b200.so.
 Instructions are matched by their index inside the kernel, so the .so must be the one profiled.
 
-    python profiles/line_profile.py gpurun_out/prof_r1g.ncu-rep bm25_select bm25 [top_n]
+    python profiles/line_profile.py gpurun_out/prof_r1g.ncu-rep bm25_select bm25 [top_n] [mangled-regex]
                                     report                       kernel-regex cubin-stem
+(mangled-regex picks the template instance in the cubin, e.g. bm25_select_kernelILb0 for <false>)
 """
 import csv
 import io
@@ -69,7 +70,7 @@ def main():
         if data[k][0] == first:
             data = data[:k]
             break
-    sl = sass_lines(stem, kre)
+    sl = sass_lines(stem, sys.argv[5] if len(sys.argv) > 5 else kre)
     if len(sl) != len(data):
         print(f"# WARNING: {len(data)} profiled SASS rows vs {len(sl)} in the current build: the .so differs from the capture")
     si, ii = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")

@@ -117,13 +117,19 @@ def test_dense_head_term_rows_match_postings():
     slot = ix.t["dense_slot"].numpy()
     df = np.diff(ix.t["term_offsets"].numpy())
     assert ((slot >= 0) == (df >= 0.25 * 3000)).all()
-    dense = ix.t["dense_impact"].numpy()
-    assert dense.shape[1] == ix.n_tiles * ix.tile_docs
-    to, pd, pi = ix.t["term_offsets"].numpy(), ix.t["post_doc"].numpy(), ix.t["post_impact"].numpy()
+    dense = ix.t["dense_impact"]
+    assert dense.dtype == torch.int16 and dense.shape[1] == ix.n_tiles * ix.tile_docs
+    # undo the per-tile interleave: 16-byte group i = docs 4i..4i+3 of the first half + 4i..4i+3 of the second
+    t8 = ix.tile_docs // 8
+    plain = dense.view(-1, ix.n_tiles, t8, 2, 4).permute(0, 1, 3, 2, 4).reshape(dense.shape[0], -1).numpy()
+    to, pd, pi = ix.t["term_offsets"].numpy(), ix.t["post_doc"].numpy(), ix.t["post_impact"].numpy().astype(np.int64)
+    sh = ix.dense_shift
+    assert 0 < plain.max() <= 16383 and (sh == 0 or plain.max() > 8191)     # 14-bit values, range used
     for t in np.flatnonzero(slot >= 0):
-        row = np.zeros(dense.shape[1], dtype=np.int32)
-        row[pd[to[t]:to[t + 1]]] = pi[to[t]:to[t + 1]]
-        assert np.array_equal(dense[slot[t]], row)
+        row = np.zeros(plain.shape[1], dtype=np.int64)
+        row[pd[to[t]:to[t + 1]]] = (pi[to[t]:to[t + 1]] + ((1 << sh) >> 1)) >> sh
+        assert np.array_equal(plain[slot[t]].astype(np.int64), row)
+    assert ix.struct().dense_shift == sh
     off = Bm25DeviceIndex.from_token_ids(offs, toks, 60, device="cpu", tile_docs=256, dense_frac=0.0)
     assert off.n_dense == 0
 
