@@ -110,10 +110,24 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     // callers guarantee all threads arrive here; s_cnt candidates sit at mbuf[kk ..)
     const int cnt = min(s_cnt, cap);
     const int n = kk + cnt;
-    const int m = next_pow2(n);
-    for (int i = n + tid; i < m; i += BM25_THREADS) mbuf[i] = 0;
-    __syncthreads();
-    block_bitonic_desc(mbuf, m, [](uint64_t a, uint64_t b) { return a < b; });
+    if (n <= BM25_THREADS) {
+      // Small merges (the common case: a few dozen survivors) rank by counting -- keys are distinct, so an
+      // element's rank is the number of larger keys: three barriers instead of a 28..36-stage sorting network.
+      const uint64_t key = tid < n ? mbuf[tid] : 0;
+      int rank = 0;
+      if (key != 0)
+        for (int j = 0; j < n; ++j) rank += mbuf[j] > key;
+      __syncthreads();
+      if (tid < kk) mbuf[tid] = 0;
+      __syncthreads();
+      if (key != 0 && rank < kk) mbuf[rank] = key;
+      __syncthreads();
+    } else {
+      const int m = next_pow2(n);
+      for (int i = n + tid; i < m; i += BM25_THREADS) mbuf[i] = 0;
+      __syncthreads();
+      block_bitonic_desc(mbuf, m, [](uint64_t a, uint64_t b) { return a < b; });
+    }
     if (tid == 0) {
       s_cnt = 0;
       unsigned long long t = mbuf[kk - 1];  // 0 while the list is not full
@@ -291,20 +305,35 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           const int cstart = incl - nch;
-          for (int c = warp; c < total; c += BM25_THREADS / 32) {
+          // software pipeline: the loads of chunk c + 8 are in flight while chunk c is added
+          uint4 d = make_uint4(0, 0, 0, 0);
+          int4 im = make_int4(0, 0, 0, 0);
+          int off = 0, slo = 0, slen = 0;   // my four postings are [off, off + 4) of the term's [slo, slen)
+          auto fetch = [&](int c, uint4& fd, int4& fi, int& foff, int& flo, int& flen) {
             const unsigned m = __ballot_sync(0xffffffffu, c >= cstart && c < incl);   // exactly one lane owns chunk c
             const int src = __ffs(m) - 1;
             const long long sa4 = __shfl_sync(0xffffffffu, a4, src);
-            const int slo = __shfl_sync(0xffffffffu, lo, src), slen = __shfl_sync(0xffffffffu, len4, src);
-            const int off = ((c - __shfl_sync(0xffffffffu, cstart, src)) << 7) + (lane << 2);
+            flo = __shfl_sync(0xffffffffu, lo, src);
+            flen = __shfl_sync(0xffffffffu, len4, src);
+            foff = ((c - __shfl_sync(0xffffffffu, cstart, src)) << 7) + (lane << 2);
+            if (foff < flen) {
+              fd = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + sa4 + foff));
+              fi = __ldg(reinterpret_cast<const int4*>(ix.d_post_impact + sa4 + foff));
+            }
+          };
+          if (warp < total) fetch(warp, d, im, off, slo, slen);
+          for (int c = warp; c < total; c += BM25_THREADS / 32) {
+            uint4 nd4 = make_uint4(0, 0, 0, 0);
+            int4 ni = make_int4(0, 0, 0, 0);
+            int noff = 0, nlo = 0, nlen = 0;
+            if (c + BM25_THREADS / 32 < total) fetch(c + BM25_THREADS / 32, nd4, ni, noff, nlo, nlen);
             if (off < slen) {
-              const uint4 d = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + sa4 + off));
-              const int4 im = __ldg(reinterpret_cast<const int4*>(ix.d_post_impact + sa4 + off));
               if (off >= slo) atomicAdd(sc + (d.x - d0u), im.x >> sh);
               if (off + 1 >= slo && off + 1 < slen) atomicAdd(sc + (d.y - d0u), im.y >> sh);
               if (off + 2 >= slo && off + 2 < slen) atomicAdd(sc + (d.z - d0u), im.z >> sh);
               if (off + 3 >= slo && off + 3 < slen) atomicAdd(sc + (d.w - d0u), im.w >> sh);
             }
+            d = nd4; im = ni; off = noff; slo = nlo; slen = nlen;
           }
         }
         __syncthreads();  // all postings of this chunk of terms are in; the staging arrays may be rewritten
