@@ -27,7 +27,7 @@ class Bm25IndexStruct(C.Structure):
                 ("impact_scale_log2", C.c_int32), ("d_term_offsets", _vp), ("d_post_doc", _vp), ("d_post_impact", _vp),
                 ("d_post_tf", _vp), ("d_tile_ptr", _vp), ("d_idf", _vp), ("d_doc_kd", _vp), ("k1_plus_1", _f64),
                 ("d_dense_slot", _vp), ("d_dense_impact", _vp), ("dense_stride", _i64), ("dense_shift", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("impacts_nonneg", C.c_int32)]
 
 
 EXPORTS = {

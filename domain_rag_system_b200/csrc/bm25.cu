@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   __shared__ Pair64 s_kth;                                               // EXACT: current k'-th best pair
   int32_t* sc = reinterpret_cast<int32_t*>(mbuf + BM25_MBUF);            // [tile_docs] fixed-point scores
   __shared__ int s_cnt;
+  __shared__ int s_note[2];   // crossing mode: documents noted in the current / previous tile (alternating)
   __shared__ unsigned long long s_tau;
   __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
   __shared__ int s_drow[BM25_TCHUNK];                        // compacted dense rows, query order
@@ -106,9 +107,9 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   const int tile_lo = int(blockIdx.x) * tiles_per_cta;
   const int cap = BM25_MBUF - kk;
 
-  auto merge = [&](int q) {
-    // callers guarantee all threads arrive here; s_cnt candidates sit at mbuf[kk ..)
-    const int cnt = min(s_cnt, cap);
+  auto merge = [&](int q, int cnt_in) {
+    // callers guarantee all threads arrive here with the same cnt_in; cnt_in candidates sit at mbuf[kk ..)
+    const int cnt = min(cnt_in, cap);
     const int n = kk + cnt;
     if (n <= BM25_THREADS) {
       // Small merges (the common case: a few dozen survivors) rank by counting -- keys are distinct, so an
@@ -170,6 +171,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     __syncthreads();
   };
 
+  if (tid < 2) s_note[tid] = 0;
+  int par = 0;
   for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
     if (EXACT && flags[q] != 1) continue;
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
@@ -179,6 +182,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     // alone, so scores stay comparable across tiles, CTAs and shards of the launch.
     const int sh = bm25_query_shift(t1 - t0);
     long long seen = 0;   // documents scanned so far for this (slice, query)
+    int cnt_list = 0;     // survivors waiting in the append area (the same value in every thread)
     if (one_chunk) stage_terms(t0, t1 - t0);
     if constexpr (EXACT) {
       for (int i = tid; i < kprime; i += BM25_THREADS) pbuf[i] = Pair64{0, -1};
@@ -200,6 +204,20 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       const int64_t rem = ix.n_docs - doc0;
       const int tile_n = rem < int64_t(T) ? int(rem) : T;
       const uint32_t d0u = uint32_t(doc0);  // tile-local index = document id - d0u
+      // Crossing mode (warm positive threshold, no negative impacts in the index): sums only grow, so a document
+      // reaches the threshold at exactly one addition -- the thread that performs it (old < tau <= new) notes the
+      // document, and the 8192-document scan after the accumulation is replaced by a look at the noted few.
+      const unsigned long long tau0 = s_tau;
+      const int tau_s0 = tau0 ? key_fx(tau0) : INT_MIN;
+      const bool cross = !EXACT && ix.impacts_nonneg != 0 && tau_s0 > 0;
+      // The noted documents are counted in s_note[par], par alternating from tile to tile: the count of tile j
+      // is read by every thread after tile j's last barrier while the early threads may already be noting for
+      // tile j+1 -- in the other counter.  Thread 0 clears a counter one tile after its use.
+      par ^= 1;
+      auto note = [&](int dl) {
+        const int pos = cnt_list + atomicAdd(&s_note[par], 1);
+        if (pos < cap) mbuf[kk + pos] = uint64_t(dl);
+      };
       // ---- accumulate ---------------------------------------------------------------------
       // Scores are integer sums of fixed-point impacts, so the order of the additions is free: the head
       // terms' dense rows are added by the thread that owns the documents (plain read-modify-write, the
@@ -225,17 +243,27 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         int4* dst = reinterpret_cast<int4*>(sc);
         const int T8 = T >> 3;
         const int dk = ix.dense_shift - sh;   // row value -> score units: << dk (>> -dk when negative)
-        auto unpack_add = [&](int4& lo4, int4& hi4, const uint4 w) {
+        auto unpack_add = [&](int4& lo4, int4& hi4, const uint4 w, int i) {
+          int4 cl, ch;   // this sweep's contribution to my eight documents
           if (dk >= 0) {
-            lo4.x += int((w.x & 0xffffu) << dk); lo4.y += int((w.x >> 16) << dk);
-            lo4.z += int((w.y & 0xffffu) << dk); lo4.w += int((w.y >> 16) << dk);
-            hi4.x += int((w.z & 0xffffu) << dk); hi4.y += int((w.z >> 16) << dk);
-            hi4.z += int((w.w & 0xffffu) << dk); hi4.w += int((w.w >> 16) << dk);
+            cl.x = int((w.x & 0xffffu) << dk); cl.y = int((w.x >> 16) << dk);
+            cl.z = int((w.y & 0xffffu) << dk); cl.w = int((w.y >> 16) << dk);
+            ch.x = int((w.z & 0xffffu) << dk); ch.y = int((w.z >> 16) << dk);
+            ch.z = int((w.w & 0xffffu) << dk); ch.w = int((w.w >> 16) << dk);
           } else {
-            lo4.x += int((w.x & 0xffffu) >> -dk); lo4.y += int((w.x >> 16) >> -dk);
-            lo4.z += int((w.y & 0xffffu) >> -dk); lo4.w += int((w.y >> 16) >> -dk);
-            hi4.x += int((w.z & 0xffffu) >> -dk); hi4.y += int((w.z >> 16) >> -dk);
-            hi4.z += int((w.w & 0xffffu) >> -dk); hi4.w += int((w.w >> 16) >> -dk);
+            cl.x = int((w.x & 0xffffu) >> -dk); cl.y = int((w.x >> 16) >> -dk);
+            cl.z = int((w.y & 0xffffu) >> -dk); cl.w = int((w.y >> 16) >> -dk);
+            ch.x = int((w.z & 0xffffu) >> -dk); ch.y = int((w.z >> 16) >> -dk);
+            ch.z = int((w.w & 0xffffu) >> -dk); ch.w = int((w.w >> 16) >> -dk);
+          }
+          lo4.x += cl.x; lo4.y += cl.y; lo4.z += cl.z; lo4.w += cl.w;
+          hi4.x += ch.x; hi4.y += ch.y; hi4.z += ch.z; hi4.w += ch.w;
+          if (cross && max(max(max(lo4.x, lo4.y), max(lo4.z, lo4.w)), max(max(hi4.x, hi4.y), max(hi4.z, hi4.w))) >= tau_s0) {
+            const int nv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+            const int cv[8] = {cl.x, cl.y, cl.z, cl.w, ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (nv[u] >= tau_s0 && nv[u] - cv[u] < tau_s0) note((u < 4 ? 0 : T / 2) + 4 * i + (u & 3));
           }
         };
         for (int g0 = 0; g0 < nd; g0 += 4) {
@@ -257,7 +285,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
               const uint4 w = make_uint4(a0.x + a1.x + a2.x + a3.x, a0.y + a1.y + a2.y + a3.y,
                                          a0.z + a1.z + a2.z + a3.z, a0.w + a1.w + a2.w + a3.w);
               int4 lo4 = tile_init ? dst[i] : z, hi4 = tile_init ? dst[T8 + i] : z;
-              unpack_add(lo4, hi4, w);
+              unpack_add(lo4, hi4, w, i);
               dst[i] = lo4;
               dst[T8 + i] = hi4;
             }
@@ -265,7 +293,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
               const uint4 w = make_uint4(b0.x + b1.x + b2.x + b3.x, b0.y + b1.y + b2.y + b3.y,
                                          b0.z + b1.z + b2.z + b3.z, b0.w + b1.w + b2.w + b3.w);
               int4 lo4 = tile_init ? dst[i2] : z, hi4 = tile_init ? dst[T8 + i2] : z;
-              unpack_add(lo4, hi4, w);
+              unpack_add(lo4, hi4, w, i2);
               dst[i2] = lo4;
               dst[T8 + i2] = hi4;
             }
@@ -277,6 +305,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           tile_init = true;
         }
         __syncthreads();   // the tile is initialised: atomics from any warp may follow
+        if (tid == 0) s_note[par ^ 1] = 0;
         // -- pass B: postings-list terms.  Rounds of 32 staged terms; inside a round the terms' postings are
         // cut into chunks of 128 (aligned groups of four per lane) and the warps take chunks round-robin.
         for (int r0 = 0; r0 < nstaged; r0 += 32) {
@@ -328,10 +357,19 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             int noff = 0, nlo = 0, nlen = 0;
             if (c + BM25_THREADS / 32 < total) fetch(c + BM25_THREADS / 32, nd4, ni, noff, nlo, nlen);
             if (off < slen) {
-              if (off >= slo) atomicAdd(sc + (d.x - d0u), im.x >> sh);
-              if (off + 1 >= slo && off + 1 < slen) atomicAdd(sc + (d.y - d0u), im.y >> sh);
-              if (off + 2 >= slo && off + 2 < slen) atomicAdd(sc + (d.z - d0u), im.z >> sh);
-              if (off + 3 >= slo && off + 3 < slen) atomicAdd(sc + (d.w - d0u), im.w >> sh);
+              auto add1 = [&](uint32_t doc, int v) {
+                const int dl = int(doc - d0u);
+                if (cross) {
+                  const int before = atomicAdd(sc + dl, v);
+                  if (before < tau_s0 && before + v >= tau_s0) note(dl);
+                } else {
+                  atomicAdd(sc + dl, v);
+                }
+              };
+              if (off >= slo) add1(d.x, im.x >> sh);
+              if (off + 1 >= slo && off + 1 < slen) add1(d.y, im.y >> sh);
+              if (off + 2 >= slo && off + 2 < slen) add1(d.z, im.z >> sh);
+              if (off + 3 >= slo && off + 3 < slen) add1(d.w, im.w >> sh);
             }
             d = nd4; im = ni; off = noff; slo = nlo; slen = nlen;
           }
@@ -399,7 +437,34 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             }
           }
         };
+        // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a tighter
+        // threshold pays for the sort, as soon as a cold list can be filled, when the append area is half full,
+        // and at the very end of this CTA's tiles.
+        auto maybe_merge = [&](bool cold, bool last) {
+          const int cnt = cnt_list;
+          if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk))) {
+            merge(q, cnt);
+            cnt_list = 0;
+          }
+        };
         int done = 0;
+        if (cross) {
+          const int cnt_now = cnt_list + s_note[par];   // the accumulation ended with a barrier
+          if (cnt_now <= cap) {        // (else: more crossings than the append area holds -- scan the ordinary way)
+            if (cnt_now > cnt_list) {  // noted documents -> keys, with their FINAL scores
+              for (int i = cnt_list + tid; i < cnt_now; i += BM25_THREADS) {
+                const int dl = int(mbuf[kk + i]);
+                const uint64_t key = make_key_fx(sc[dl], uint32_t(doc0 + dl));
+                mbuf[kk + i] = key > tau0 ? key : 0;
+              }
+              __syncthreads();
+            }
+            cnt_list = cnt_now;
+            done = T;
+            seen += T;
+            maybe_merge(false, j == tile_lo);
+          }
+        }
         while (done < T) {
           const bool cold = (s_tau == 0);
           // Steps grow geometrically with the number of documents this (slice, query) has seen: a step of 3x the
@@ -408,7 +473,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           long long want = grow > BM25_COLD_STEP ? grow : BM25_COLD_STEP;
           if (want > T - done) want = T - done;
           const int step = cold ? BM25_COLD_STEP : int(want);
-          const int cnt_before = s_cnt;
+          if (tid == 0) s_cnt = cnt_list;
           __syncthreads();
           scan_range(done, step);
           __syncthreads();
@@ -416,23 +481,18 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             // more survivors than the append area holds (some were dropped): redo the range in segments
             // that cannot overflow, merging whenever the area fills up
             __syncthreads();
-            if (tid == 0) s_cnt = cnt_before;
+            if (tid == 0) s_cnt = cnt_list;
             __syncthreads();
             for (int d2 = done; d2 < done + step; d2 += BM25_SEG) {
-              if (s_cnt > cap - BM25_SEG) merge(q);
+              if (s_cnt > cap - BM25_SEG) merge(q, s_cnt);
               scan_range(d2, min(BM25_SEG, done + step - d2));
               __syncthreads();
             }
           }
+          cnt_list = s_cnt;
           done += step;
           seen += step;
-          // Merge (sort list + survivors, tighten the threshold) when enough survivors piled up that a
-          // tighter threshold pays for the sort, as soon as a cold list can be filled, when the append
-          // area is half full, and at the very end of this CTA's tiles.
-          const bool last = (done >= T) && (j == tile_lo);
-          const int cnt = s_cnt;
-          if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk)))
-            merge(q);
+          maybe_merge(cold, (done >= T) && (j == tile_lo));
         }
       }
     }

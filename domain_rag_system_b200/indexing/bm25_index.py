@@ -64,6 +64,7 @@ class Bm25DeviceIndex:
         self.n_dense = 0                           # head terms that also have a dense impact row
         self.impact_scale_log2 = 0                 # stored impacts = round(impact * 2^s)
         self.dense_shift = 0                       # dense row value = round(stored impact / 2^dense_shift)
+        self.impacts_nonneg = 0                    # 1: no negative impact anywhere (enables crossing detection)
         self.t: Dict[str, torch.Tensor] = {}       # device tensors
         self._struct = None
 
@@ -171,6 +172,7 @@ class Bm25DeviceIndex:
         self.impact_scale_log2 = int(min(40, math.floor(IMPACT_BITS - math.log2(max_imp)))) if max_imp > 0 else 0
         impact = torch.round(impact64 * float(2.0 ** self.impact_scale_log2)).clamp_(-2 ** IMPACT_BITS, 2 ** IMPACT_BITS)
         impact = impact.to(torch.int32)
+        self.impacts_nonneg = int(impact.numel() == 0 or int(impact.min()) >= 0)
         del impact64
         if int(tf.max()) > 65535:
             raise NotImplementedError("term frequency above 65535 in one chunk")
@@ -274,6 +276,7 @@ class Bm25DeviceIndex:
             s.d_dense_impact = t["dense_impact"].data_ptr()
             s.dense_stride = self.n_tiles * self.tile_docs
             s.dense_shift = self.dense_shift
+            s.impacts_nonneg = self.impacts_nonneg
             self._struct = s
         return self._struct
 
@@ -318,7 +321,7 @@ class Bm25DeviceIndex:
                              average_idf=self.average_idf, vocab_present=self.vocab_present,
                              total_tokens=self.total_tokens, row_offset=self.row_offset,
                              impact_scale_log2=self.impact_scale_log2, n_dense=self.n_dense,
-                             dense_shift=self.dense_shift,
+                             dense_shift=self.dense_shift, impacts_nonneg=self.impacts_nonneg,
                              n_docs_global=self.n_docs_global),
                 "vocab": self.vocab, "tensors": {k: v.cpu() for k, v in self.t.items()}}
 

@@ -117,7 +117,9 @@ typedef struct drs_bm25_index {
   const uint16_t* d_dense_impact;/* [n_dense, dense_stride]                              */
   int64_t dense_stride;         /* n_tiles * tile_docs (rows are zero padded)            */
   int32_t dense_shift;          /* row value * 2^dense_shift ~ stored impact             */
-  int32_t reserved;
+  int32_t impacts_nonneg;       /* 1 = no stored impact is negative (no negative idf floor): scores only
+                                   grow while a tile accumulates, which lets the kernel catch threshold
+                                   crossings instead of scanning the tile; 0 is always safe         */
 } drs_bm25_index;
 
 /* ---------------------------------------------------------------------------------
