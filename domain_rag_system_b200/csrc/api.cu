@@ -182,7 +182,12 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   }
   if (rc != DRS_OK) return rc;
   ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-  rc = launch_merge_keys(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, scratch, st);
+  {
+    // the kernel's own thresholds (gtau, and the per-slab pooled bounds when pooling was on) pre-filter the merge
+    const uint32_t* gtau = reinterpret_cast<const uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off);
+    rc = launch_merge_keys_filtered(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, scratch, gtau,
+                                    gtau + w.umma_qstride, w.umma_parts, w.umma_qstride, st);
+  }
   if (rc != DRS_OK) return rc;
   rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
                             d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st);

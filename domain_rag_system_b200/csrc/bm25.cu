@@ -532,20 +532,56 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
   __shared__ int s_valid;
   const int q = blockIdx.x, c = threadIdx.x;
   const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
-  uint64_t okey = 0;
+  // One thread per (candidate, query token): the posting lookup is a ~13-step binary search of dependent loads,
+  // so the candidates' terms are looked up side by side (8 tokens per round) and then added by the candidate's
+  // own thread in query order -- the same fp64 operations in the same order as bm25_exact_score.
+  constexpr int RT = 8;
+  __shared__ double s_contrib[256 * RT];   // NaN = the document does not contain the term
   int64_t doc = -1;
-  double score = 0.0;
   if (c < kk) {
     const uint64_t key = cand[size_t(q) * kk + c];
-    if (key != 0) {
-      doc = key_row(key);
-      score = bm25_exact_score(ix, q_terms, t0, t1, doc);
-      okey = ord64(score);
-    }
+    if (key != 0) doc = key_row(key);
   }
-  skey[c] = okey;
   sdoc[c] = doc;
   if (c == 0) s_valid = 0;
+  __syncthreads();
+  double score = 0.0;
+  for (int r0 = t0; r0 < t1; r0 += RT) {
+    const int nr = min(RT, t1 - r0);
+    for (int pair = c; pair < kk * nr; pair += blockDim.x) {
+      const int ci = pair / nr, ti = pair - ci * nr;
+      const int64_t d = sdoc[ci];
+      double contrib = __longlong_as_double(0x7ff8000000000000ll);
+      const int t = q_terms[r0 + ti];
+      if (d >= 0 && t >= 0 && t < ix.n_terms) {
+        const int j = int(d / ix.tile_docs);
+        const int64_t base = ix.d_term_offsets[t];
+        const uint32_t* tp = ix.d_tile_ptr + size_t(t) * (ix.n_tiles + 1) + j;
+        const int64_t end = base + tp[1];
+        int64_t lo = base + tp[0], hi = end;  // [lo, hi)
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (ix.d_post_doc[mid] < uint32_t(d)) lo = mid + 1;
+          else hi = mid;
+        }
+        if (lo < end && ix.d_post_doc[lo] == uint32_t(d)) {
+          const double tf = double(ix.d_post_tf[lo]);
+          contrib = __dmul_rn(ix.d_idf[t], __ddiv_rn(__dmul_rn(tf, ix.k1_plus_1), __dadd_rn(tf, ix.d_doc_kd[d])));
+        }
+      }
+      s_contrib[ci * RT + ti] = contrib;
+    }
+    __syncthreads();
+    if (c < kk && doc >= 0) {
+      for (int ti = 0; ti < nr; ++ti) {
+        const double v = s_contrib[c * RT + ti];
+        if (v == v) score = __dadd_rn(score, v);
+      }
+    }
+    __syncthreads();
+  }
+  const uint64_t okey = doc >= 0 ? ord64(score) : 0;
+  skey[c] = okey;
   __syncthreads();
   if (c < kk && doc >= 0) {
     int rank = 0;

@@ -145,6 +145,9 @@ __host__ __device__ __forceinline__ int cand_len_umma(int kprime) { return kprim
 size_t merge_scratch_keys(int n_parts, int n_queries, int kk);   // scratch a two-level merge needs (keys)
 int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
                       uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, cudaStream_t st);
+int launch_merge_keys_filtered(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
+                               uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, const uint32_t* d_tau32,
+                               const uint32_t* d_pool, int n_pool, int pool_stride, cudaStream_t st);
 int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                          int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,

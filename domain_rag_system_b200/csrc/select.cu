@@ -17,16 +17,68 @@ constexpr int MERGE_BUF = 2048;
 constexpr int MERGE_FANIN = 16;       // parts per CTA in the first level of a two-level merge
 constexpr int MERGE_TWO_LEVEL = 48;   // more parts than this => two levels
 
+// Optional pre-filter (the tensor-core kernel's thresholds): tau32[q] and min over pool[s * pool_stride + q]
+// (if every entry is set) are ordered-u32 LOWER bounds of query q's kk-th best score, so keys scoring below them
+// cannot be among the kk best.  Usually a few dozen of the ~1300 keys survive, and a rank-by-counting pass
+// (keys are distinct: rank = number of larger keys) replaces the 2048-key sorting network.
 __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restrict__ parts, int n_parts,
                                                          int q_stride, int kk, uint64_t* __restrict__ out,
                                                          int out_qstride, const int32_t* __restrict__ active,
-                                                         int ppc) {
+                                                         int ppc, const uint32_t* __restrict__ tau32,
+                                                         const uint32_t* __restrict__ pool, int n_pool,
+                                                         int pool_stride) {
   __shared__ uint64_t buf[MERGE_BUF];
+  __shared__ unsigned s_bound;
+  __shared__ int s_n;
   const int q = blockIdx.x;
   if (active != nullptr && active[q] == 0) return;
   const int p0 = blockIdx.y * ppc;
   const int np = min(ppc, n_parts - p0);
   const int n = np * kk;
+  if (tau32 != nullptr && kk <= 256) {
+    if (threadIdx.x == 0) {
+      s_bound = 0xffffffffu;
+      s_n = 0;
+    }
+    __syncthreads();
+    if (pool != nullptr && n_pool > 0) {
+      unsigned mn = 0xffffffffu;
+      for (int i = threadIdx.x; i < n_pool; i += blockDim.x) mn = min(mn, pool[size_t(i) * pool_stride + q]);
+      for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if ((threadIdx.x & 31) == 0) atomicMin(&s_bound, mn);
+    }
+    __syncthreads();
+    unsigned bound = tau32[q];
+    if (pool != nullptr && n_pool > 0 && s_bound != 0u) bound = max(bound, s_bound);   // 0: a slab never reported
+    for (int f = threadIdx.x; f < n; f += blockDim.x) {
+      const int p = f / kk, c = f - p * kk;
+      const uint64_t v = parts[(size_t(p0 + p) * q_stride + q) * kk + c];
+      if (v != 0 && unsigned(v >> 32) >= bound) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < MERGE_BUF) buf[pos] = v;
+      }
+    }
+    __syncthreads();
+    const int ns = s_n;
+    if (ns <= MERGE_BUF) {
+      if (ns <= 256) {
+        const uint64_t key = int(threadIdx.x) < ns ? buf[threadIdx.x] : 0;
+        int rank = 0;
+        if (key != 0)
+          for (int j = 0; j < ns; ++j) rank += buf[j] > key;
+        for (int i = ns + threadIdx.x; i < kk; i += blockDim.x) out[(size_t(blockIdx.y) * out_qstride + q) * kk + i] = 0;
+        if (key != 0 && rank < kk) out[(size_t(blockIdx.y) * out_qstride + q) * kk + rank] = key;
+      } else {
+        const int m = next_pow2(ns);
+        for (int i = ns + threadIdx.x; i < m; i += blockDim.x) buf[i] = 0;
+        __syncthreads();
+        block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
+        for (int i = threadIdx.x; i < kk; i += blockDim.x) out[(size_t(blockIdx.y) * out_qstride + q) * kk + i] = buf[i];
+      }
+      return;
+    }
+    __syncthreads();   // more survivors than the buffer holds (thresholds unset): the general path below
+  }
   for (int i = threadIdx.x; i < kk; i += blockDim.x) buf[i] = 0;
   int pos = 0;
   while (pos < n) {
@@ -55,24 +107,31 @@ size_t merge_scratch_keys(int n_parts, int n_queries, int kk) {
   return size_t((n_parts + MERGE_FANIN - 1) / MERGE_FANIN) * n_queries * kk;
 }
 
-int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
-                      uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, cudaStream_t st) {
+int launch_merge_keys_filtered(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
+                               uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, const uint32_t* d_tau32,
+                               const uint32_t* d_pool, int n_pool, int pool_stride, cudaStream_t st) {
   DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2, DRS_ERR_UNSUPPORTED, "merge: list length out of range");
   if (n_parts > MERGE_TWO_LEVEL && d_scratch != nullptr) {
     const int g1 = (n_parts + MERGE_FANIN - 1) / MERGE_FANIN;
     merge_keys_kernel<<<dim3(n_queries, g1), 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_scratch, n_queries,
-                                                            d_active, MERGE_FANIN);
+                                                            d_active, MERGE_FANIN, d_tau32, d_pool, n_pool, pool_stride);
     count_launches(1);
     merge_keys_kernel<<<dim3(n_queries, 1), 256, 0, st>>>(d_scratch, g1, n_queries, kk, d_out, n_queries, d_active,
-                                                           g1);
+                                                           g1, nullptr, nullptr, 0, 0);
     count_launches(1);
   } else {
     merge_keys_kernel<<<dim3(n_queries, 1), 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_out, n_queries, d_active,
-                                                           n_parts);
+                                                           n_parts, d_tau32, d_pool, n_pool, pool_stride);
     count_launches(1);
   }
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;
+}
+
+int launch_merge_keys(const uint64_t* d_parts, int n_parts, int q_stride, int n_queries, int kk,
+                      uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, cudaStream_t st) {
+  return launch_merge_keys_filtered(d_parts, n_parts, q_stride, n_queries, kk, d_out, d_active, d_scratch, nullptr,
+                                    nullptr, 0, 0, st);
 }
 
 // ------------------------------------------------------------------------------------------
