@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
     unsigned long long* __restrict__ gtau, const int32_t* __restrict__ flags, const int32_t* __restrict__ fx_low,
-    int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids) {
+    int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids, int* __restrict__ next_query) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
   Pair64* pbuf = reinterpret_cast<Pair64*>(smem_raw);                    // EXACT: [BM25_MBUF / 2] (score, doc) pairs
@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   int32_t* sc = reinterpret_cast<int32_t*>(mbuf + BM25_MBUF);            // [tile_docs] fixed-point scores
   __shared__ int s_cnt;
   __shared__ int s_note[2];   // crossing mode: documents noted in the current / previous tile (alternating)
+  __shared__ int s_q;         // the query this CTA works on (handed out by next_query[slice])
   __shared__ unsigned long long s_tau;
   __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
   __shared__ int s_drow[BM25_TCHUNK];                        // compacted dense rows, query order
@@ -173,7 +174,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
 
   if (tid < 2) s_note[tid] = 0;
   int par = 0;
-  for (int q = blockIdx.y; q < n_queries; q += gridDim.y) {
+  // Queries are handed out dynamically per slice (an atomic counter): queries differ in cost (number of terms,
+  // their document frequencies), and a static split leaves the CTAs that drew one query more than the others
+  // working alone at the end.
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_q = atomicAdd(next_query + blockIdx.x, 1);
+    __syncthreads();
+    const int q = s_q;
+    if (q >= n_queries) break;
     if (EXACT && flags[q] != 1) continue;
     const int t0 = q_offsets[q], t1 = q_offsets[q + 1];
     const bool one_chunk = (t1 - t0) <= BM25_TCHUNK;
@@ -668,7 +677,7 @@ static Bm25Ws bm25_ws(int n_queries, int gx, int kk, int kprime) {
   };
   w.parts = take(size_t(gx) * n_queries * kk * 8);
   w.cand = take(size_t(n_queries) * kk * 8);
-  w.gtau = take(size_t(n_queries) * 8);
+  w.gtau = take(size_t(n_queries) * 8 + size_t(2 * gx) * 4);   // thresholds, then the two passes' query counters
   w.mscratch = take(merge_scratch_keys(gx, n_queries, kk) * 8);
   w.flags = take(size_t(n_queries) * 4);
   w.fxlow = take(size_t(n_queries) * 4);
@@ -715,14 +724,16 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   int32_t* fxlow = reinterpret_cast<int32_t*>(base + w.fxlow);
   double* escores = reinterpret_cast<double*>(base + w.escores);
   int64_t* eids = reinterpret_cast<int64_t*>(base + w.eids);
-  DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8, st));
+  int* next_query = reinterpret_cast<int*>(gtau + n_queries);   // [2][gx]
+  DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8 + size_t(2 * gx) * 4, st));
   const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
   DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
     bm25_select_kernel<false><<<dim3(gx, gy), BM25_THREADS, smem, st>>>(
-        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr);
+        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr,
+        next_query);
     count_launches(1);
   }
   DRS_CUDA_CHECK(cudaGetLastError());
@@ -736,7 +747,8 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   if (mode != 1) {
     // escalation, predicated on the device-side flags (no host round trip): CTAs of proven queries exit at once
     bm25_select_kernel<true><<<dim3(gx, gy), BM25_THREADS, smem, st>>>(
-        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids);
+        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
+        next_query + gx);
     count_launches(1);
     DRS_CUDA_CHECK(cudaGetLastError());
     rc = launch_merge_pairs_f64(escores, eids, gx, n_queries, kprime, kprime, d_out_scores, d_out_ids, flags, st);
