@@ -255,11 +255,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         for (int ks = 0; ks < kst; ++ks) {
           mbar_wait(empty + s, ph ^ 1, 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(full + s, STAGE_BYTES);
+            // debug bit 4 (timing experiment only, results are garbage): fetch half of every stage
+            const int nb = (p.debug & 4) ? NBOX / 2 : NBOX;
+            mbar_arrive_expect_tx(full + s, uint32_t(nb) * BOX_BYTES);
             uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
 #pragma unroll
             for (int b = 0; b < NBOX; ++b)
-              tma_load_2d(&tmap, full + s, dst + b * BOX_BYTES, ks * STAGE_K + b * BOX_K, t * TILE_N);
+              if (b < nb) tma_load_2d(&tmap, full + s, dst + b * BOX_BYTES, ks * STAGE_K + b * BOX_K, t * TILE_N);
           }
           __syncwarp();
           if (++s == uint32_t(p.n_stages)) {
@@ -296,7 +298,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
             for (int k16 = 0; k16 < STAGE_K / 16; ++k16) {
               // +32 bytes per K=16 step inside a 128-byte swizzle row, +8 KB for the second box
               const uint64_t b_desc = desc0 + uint64_t((k16 >> 2) * (BOX_BYTES >> 4) + (k16 & 3) * 2);
-              umma_ts(d_tmem, a0 + k16 * 8, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
+              // debug bit 8 (timing experiment only): issue every other MMA
+              if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(d_tmem, a0 + k16 * 8, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
             }
             tc_commit(empty + s);                      // the stage is free once these MMAs have read it
             if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
@@ -399,12 +402,15 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         tc_fence_after();
         uint32_t acc0[32], acc1[32];
         const uint32_t taddr = tmem_base + lane_addr + ACC_COL0 + as * TILE_N;
-        tmem_ld32(taddr, acc0);
-        tmem_ld32(taddr + 32, acc1);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!(p.debug & 32)) {   // debug bit 32 (timing experiment): skip the accumulator read
+          tmem_ld32(taddr, acc0);
+          tmem_ld32(taddr + 32, acc1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         // ---- pass 1, branch-free: which of my 64 scores reach the threshold?
         uint32_t m0 = 0, m1 = 0;
         const float4* nb4 = reinterpret_cast<const float4*>(nbuf);
+        if (!(p.debug & 16)) {   // debug bit 16 (timing experiment): skip pass 1
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const float4 n = nb4[g];
@@ -420,6 +426,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
           m1 |= (__uint_as_float(acc1[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
           m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
           m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+        }
         }
         if (no_insert) m0 = m1 = 0;
         // ---- pass 2, rare and rolled.  2a: for every column some lane flagged, all lanes re-read that one
