@@ -299,7 +299,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
               // +32 bytes per K=16 step inside a 128-byte swizzle row, +8 KB for the second box
               const uint64_t b_desc = desc0 + uint64_t((k16 >> 2) * (BOX_BYTES >> 4) + (k16 & 3) * 2);
               // debug bit 8 (timing experiment only): issue every other MMA
-              if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(d_tmem, a0 + k16 * 8, b_desc, IDESC, (ks | k16) != 0 ? 1u : 0u);
+              // debug bits 64 / 128 (timing experiments): N = 32 / N = 128 instead of 64 per MMA
+              const uint32_t idesc = (p.debug & 64) ? ((IDESC & ~(0x3fu << 17)) | (4u << 17))
+                                                    : ((p.debug & 128) ? ((IDESC & ~(0x3fu << 17)) | (16u << 17)) : IDESC);
+              // debug bit 256 (timing experiment): consecutive MMAs alternate between the two accumulator stages
+              const uint32_t dd = (p.debug & 128) ? tmem_base + ACC_COL0
+                                                  : ((p.debug & 256) ? tmem_base + ACC_COL0 + (k16 & 1) * TILE_N : d_tmem);
+              if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(dd, a0 + k16 * 8, b_desc, idesc, (ks | k16) != 0 ? 1u : 0u);
             }
             tc_commit(empty + s);                      // the stage is free once these MMAs have read it
             if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
@@ -543,6 +549,8 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   if (fixed + size_t(pl.nbox == 4 ? 3 : MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
   if (ns > 24 / pl.nbox) ns = 24 / pl.nbox;
+  static const int cap_stages = [] { const char* e = getenv("DRS_UMMA_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
+  if (cap_stages > 0 && ns > cap_stages) ns = cap_stages;
   pl.n_stages = ns;
   pl.smem = fixed + size_t(ns) * STAGE_BYTES;
   pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
