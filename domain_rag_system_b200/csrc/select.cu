@@ -35,6 +35,48 @@ __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restr
   const int p0 = blockIdx.y * ppc;
   const int np = min(ppc, n_parts - p0);
   const int n = np * kk;
+  // Many lists and no published threshold (single-query latency mode: every CTA of the selection kernel hands in
+  // a list): the kk-th largest of the lists' MAXIMA is a lower bound of the kk-th best key (kk different lists
+  // each hold a key at least that large), so everything below it is dropped before any sorting.
+  if (tau32 == nullptr && np >= kk && np > MERGE_TWO_LEVEL && np <= MERGE_BUF && kk <= 256) {
+    __shared__ uint64_t s_kbound;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int p = warp; p < np; p += nw) {
+      uint64_t mx = 0;
+      for (int c = lane; c < kk; c += 32) mx = max(mx, parts[(size_t(p0 + p) * q_stride + q) * kk + c]);
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) buf[p] = mx;
+    }
+    const int mp = next_pow2(np);
+    for (int i = np + threadIdx.x; i < mp; i += blockDim.x) buf[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    block_bitonic_desc(buf, mp, [](uint64_t a, uint64_t b) { return a < b; });
+    if (threadIdx.x == 0) s_kbound = buf[kk - 1];
+    __syncthreads();
+    const uint64_t kb = s_kbound;
+    if (kb != 0) {
+      for (int f = threadIdx.x; f < n; f += blockDim.x) {
+        const int p = f / kk, c = f - p * kk;
+        const uint64_t v = parts[(size_t(p0 + p) * q_stride + q) * kk + c];
+        if (v >= kb) {
+          const int pos = atomicAdd(&s_n, 1);
+          if (pos < MERGE_BUF) buf[pos] = v;
+        }
+      }
+      __syncthreads();
+      const int ns = s_n;
+      if (ns <= MERGE_BUF) {
+        const int m = next_pow2(max(ns, kk));
+        for (int i = ns + threadIdx.x; i < m; i += blockDim.x) buf[i] = 0;
+        __syncthreads();
+        block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
+        for (int i = threadIdx.x; i < kk; i += blockDim.x) out[(size_t(blockIdx.y) * out_qstride + q) * kk + i] = buf[i];
+        return;
+      }
+    }
+    __syncthreads();   // fewer than kk non-empty lists, or too many survivors: the general path below
+  }
   if (tau32 != nullptr && kk <= 256) {
     if (threadIdx.x == 0) {
       s_bound = 0xffffffffu;
@@ -111,7 +153,8 @@ int launch_merge_keys_filtered(const uint64_t* d_parts, int n_parts, int q_strid
                                uint64_t* d_out, const int32_t* d_active, uint64_t* d_scratch, const uint32_t* d_tau32,
                                const uint32_t* d_pool, int n_pool, int pool_stride, cudaStream_t st) {
   DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2, DRS_ERR_UNSUPPORTED, "merge: list length out of range");
-  if (n_parts > MERGE_TWO_LEVEL && d_scratch != nullptr) {
+  const bool bounded_single = d_tau32 == nullptr && n_parts >= kk && n_parts <= MERGE_BUF && kk <= 256;
+  if (n_parts > MERGE_TWO_LEVEL && d_scratch != nullptr && !bounded_single) {
     const int g1 = (n_parts + MERGE_FANIN - 1) / MERGE_FANIN;
     merge_keys_kernel<<<dim3(n_queries, g1), 256, 0, st>>>(d_parts, n_parts, q_stride, kk, d_scratch, n_queries,
                                                             d_active, MERGE_FANIN, d_tau32, d_pool, n_pool, pool_stride);
