@@ -57,7 +57,9 @@ def stall_summary(rep, kernel_regex):
     hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
     if not hi:
         return
-    hdr, data = rows[hi[0]], rows[hi[0] + 1:]
+    end = hi[1] if len(hi) > 1 else len(rows)          # several kernels may match: keep the first one's rows
+    hdr = rows[hi[0]]
+    data = [r for r in rows[hi[0] + 1:end] if len(r) == len(hdr)]
     si, ii = hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
     cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     tot = sum(num(r[si]) for r in data) or 1.0
