@@ -101,6 +101,79 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tmap, uint64_t* b
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_remote(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// the same bounded wait, for barriers the peer CTA arrives on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("drs dense_umma(pair): barrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
+             threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+// TMA load into THIS CTA's shared memory that signals a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tmap, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// commit of cta_group::2 MMAs: arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+// D[tmem, 256 x N over the pair] (+)= A[tmem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // one lane of a fully converged warp
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -193,10 +266,19 @@ __device__ __forceinline__ uint64_t heap_replace_root(uint32_t lst, int kk, uint
 
 // NBOX = 64-wide TMA boxes per ring stage.  A stage is the unit of the full/empty handshake: with 4 boxes
 // (K = 256 per stage) the MMA warp pays one barrier round trip per 16 MMAs instead of per 8.
-template <int NBOX>
+// PAIR = two CTAs of a cluster (one TPC) share every MMA (cta_group::2): each holds ITS OWN block of 128 queries in
+// its tensor memory and HALF of every 64-row corpus tile in its shared memory; the leader CTA issues M = 256 MMAs
+// whose accumulator rows 0..127 land in the leader's TMEM and 128..255 in the peer's.  The fixed per-MMA cost is
+// paid once for two query blocks and every shared-memory byte feeds twice the math.
+template <int NBOX, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
   constexpr int STAGE_K = NBOX * BOX_K;
-  constexpr int STAGE_BYTES = NBOX * BOX_BYTES;
+  constexpr int BOXB = PAIR ? BOX_BYTES / 2 : BOX_BYTES;   // a box is 64 K-elements x 64 (32 in a pair) rows
+  constexpr int STAGE_BYTES = NBOX * BOXB;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader
+  const int cta = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);       // work-item stream this CTA (pair) walks
+  const int n_ctas = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int nqbx = PAIR ? (p.nqb + 1) / 2 : p.nqb;         // query blocks (pairs of blocks) per slab
   extern __shared__ uint8_t smem_dyn[];
   // carve: [ring | lists | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -212,31 +294,41 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       (reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = p.nqb * p.n_slabs;
+  const int n_items = nqbx * p.n_slabs;
   const int kst = p.dim / STAGE_K;  // smem stages per accumulator tile
 
   if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
   if (warp == 1 && lane == 0) {
+    // In a pair the leader's full / tempty / a_ready barriers collect the arrivals of BOTH CTAs; empty and tfull
+    // are signalled in each CTA by the multicast commit.
     for (int s = 0; s < p.n_stages; ++s) {
-      mbar_init(full + s, 1);
+      mbar_init(full + s, PAIR ? 2 : 1);
       mbar_init(empty + s, 1);
     }
     mbar_init(tfull + 0, 1);
     mbar_init(tfull + 1, 1);
-    mbar_init(tempty + 0, 4);
-    mbar_init(tempty + 1, 4);
-    mbar_init(a_ready, 4 * p.n_groups);
+    mbar_init(tempty + 0, PAIR ? 8 : 4);
+    mbar_init(tempty + 1, PAIR ? 8 : 4);
+    mbar_init(a_ready, (PAIR ? 8 : 4) * p.n_groups);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(uint32_t(TMEM_COLS))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(uint32_t(TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(uint32_t(TMEM_COLS))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
@@ -248,20 +340,30 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
   if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t s = 0, ph = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    for (int item = cta; item < n_items; item += n_ctas) {
       int t0, t1;
-      slab_tiles(item / p.nqb, t0, t1);
+      slab_tiles(item / nqbx, t0, t1);
       for (int t = t0; t < t1; ++t) {
         for (int ks = 0; ks < kst; ++ks) {
           mbar_wait(empty + s, ph ^ 1, 1);
           if (elect_one()) {
             // debug bit 4 (timing experiment only, results are garbage): fetch half of every stage
             const int nb = (p.debug & 4) ? NBOX / 2 : NBOX;
-            mbar_arrive_expect_tx(full + s, uint32_t(nb) * BOX_BYTES);
             uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
+            if constexpr (PAIR) {
+              // my half of the tile (rows 32*rank ..) goes to MY ring; the bytes are counted by the LEADER's barrier
+              const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);
+              mbar_arrive_expect_tx_remote(lbar, uint32_t(nb) * BOXB);
 #pragma unroll
-            for (int b = 0; b < NBOX; ++b)
-              if (b < nb) tma_load_2d(&tmap, full + s, dst + b * BOX_BYTES, ks * STAGE_K + b * BOX_K, t * TILE_N);
+              for (int b = 0; b < NBOX; ++b)
+                if (b < nb)
+                  tma_load_2d_pair(&tmap, lbar, dst + b * BOXB, ks * STAGE_K + b * BOX_K, t * TILE_N + int(rank) * (TILE_N / 2));
+            } else {
+              mbar_arrive_expect_tx(full + s, uint32_t(nb) * BOXB);
+#pragma unroll
+              for (int b = 0; b < NBOX; ++b)
+                if (b < nb) tma_load_2d(&tmap, full + s, dst + b * BOXB, ks * STAGE_K + b * BOX_K, t * TILE_N);
+            }
           }
           __syncwarp();
           if (++s == uint32_t(p.n_stages)) {
@@ -271,25 +373,29 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ===================================================================== MMA issuer (the leader CTA of a pair)
     // The WHOLE warp walks the loops (so every address below is warp-uniform and lives in uniform
     // registers); one elected lane issues the tcgen05 instructions.  A tile's 48 MMAs take 32 tensor
     // cycles each, so the issue path must stay within a handful of instructions per MMA.
     uint32_t st = 0, it = 0, item_idx = 0;
     uint32_t s = 0, ph = 0;   // ring slot / phase, stepped without divisions
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_idx) {
+    constexpr uint32_t IDESC_PAIR = (IDESC & ~(0x1fu << 24)) | (uint32_t((2 * BLOCK_M) >> 4) << 24);   // M = 256
+    for (int item = cta; item < n_items; item += n_ctas, ++item_idx) {
       int t0, t1;
-      slab_tiles(item / p.nqb, t0, t1);
-      mbar_wait(a_ready, item_idx & 1, 2);
+      slab_tiles(item / nqbx, t0, t1);
+      if constexpr (PAIR) mbar_wait_cluster(a_ready, item_idx & 1, 2);
+      else mbar_wait(a_ready, item_idx & 1, 2);
       tc_fence_after();
       for (int t = t0; t < t1; ++t, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(tempty + as, aph ^ 1, 3);
+        if constexpr (PAIR) mbar_wait_cluster(tempty + as, aph ^ 1, 3);
+        else mbar_wait(tempty + as, aph ^ 1, 3);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ACC_COL0 + as * TILE_N;
         for (int ks = 0; ks < kst; ++ks, ++st) {
-          mbar_wait(full + s, ph, 4);
+          if constexpr (PAIR) mbar_wait_cluster(full + s, ph, 4);
+          else mbar_wait(full + s, ph, 4);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t desc0 = make_b_desc(smem_u32(ring + size_t(s) * STAGE_BYTES));
@@ -297,7 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
 #pragma unroll
             for (int k16 = 0; k16 < STAGE_K / 16; ++k16) {
               // +32 bytes per K=16 step inside a 128-byte swizzle row, +8 KB for the second box
-              const uint64_t b_desc = desc0 + uint64_t((k16 >> 2) * (BOX_BYTES >> 4) + (k16 & 3) * 2);
+              const uint64_t b_desc = desc0 + uint64_t((k16 >> 2) * (BOXB >> 4) + (k16 & 3) * 2);
               // debug bit 8 (timing experiment only): issue every other MMA
               // debug bits 64 / 128 (timing experiments): N = 32 / N = 128 instead of 64 per MMA
               const uint32_t idesc = (p.debug & 64) ? ((IDESC & ~(0x3fu << 17)) | (4u << 17))
@@ -305,10 +411,19 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
               // debug bit 256 (timing experiment): consecutive MMAs alternate between the two accumulator stages
               const uint32_t dd = (p.debug & 128) ? tmem_base + ACC_COL0
                                                   : ((p.debug & 256) ? tmem_base + ACC_COL0 + (k16 & 1) * TILE_N : d_tmem);
-              if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(dd, a0 + k16 * 8, b_desc, idesc, (ks | k16) != 0 ? 1u : 0u);
+              if constexpr (PAIR) {
+                umma_ts_pair(d_tmem, a0 + k16 * 8, b_desc, IDESC_PAIR, (ks | k16) != 0 ? 1u : 0u);
+              } else {
+                if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(dd, a0 + k16 * 8, b_desc, idesc, (ks | k16) != 0 ? 1u : 0u);
+              }
             }
-            tc_commit(empty + s);                      // the stage is free once these MMAs have read it
-            if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
+            if constexpr (PAIR) {
+              tc_commit_pair(empty + s);                      // frees the stage in both CTAs
+              if (ks == kst - 1) tc_commit_pair(tfull + as);  // both CTAs' halves of the accumulator are complete
+            } else {
+              tc_commit(empty + s);                      // the stage is free once these MMAs have read it
+              if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
+            }
           }
           __syncwarp();
           if (++s == uint32_t(p.n_stages)) {
@@ -331,8 +446,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
     const uint32_t mylist = smem_u32(lists) + uint32_t(grp * p.kk * BLOCK_M + L) * 8;  // my heap's slot 0
     float* norm_strip = norm_strips + (warp - 4) * 2 * TILE_N;
     uint32_t it = 0;                         // tiles issued so far (both groups), mirrors the MMA warp
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int qb = item % p.nqb, slab = item / p.nqb;
+    const uint32_t a_ready_leader = PAIR ? mapa_u32(smem_u32(a_ready), 0) : 0u;
+    const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(tempty), 0) : 0u;
+    for (int item = cta; item < n_items; item += n_ctas) {
+      const int qb = PAIR ? 2 * (item % nqbx) + int(rank) : item % nqbx, slab = item / nqbx;
       int t0, t1;
       slab_tiles(slab, t0, t1);
       // ---- queries -> bf16 -> TMEM (A operand), 64 elements (32 columns) at a time
@@ -355,7 +472,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_remote(a_ready_leader);
+        else mbar_arrive(a_ready);
+      }
       // ---- private top-kk min-heap; its root is the kk-th best candidate once the list is full
       for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
       uint64_t root = 0;
@@ -488,7 +608,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty + as);  // accumulator stage may be overwritten
+        if (lane == 0) {                          // accumulator stage may be overwritten
+          if constexpr (PAIR) mbar_arrive_remote(tempty_leader + as * 8);
+          else mbar_arrive(tempty + as);
+        }
         // ---- 2b
         if (nst > 0) insert(s0, j0);
         if (nst > 1) insert(s1, j1);
@@ -497,17 +620,24 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       }
       it += uint32_t(t1 - t0);
       // ---- hand the list over
-      uint64_t* dst = p.parts + (size_t(vslab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
-      for (int c = 0; c < p.kk; ++c) dst[c] = lds_u64(mylist + c * LSTRIDE);
+      if (qb < p.nqb) {   // (the odd block out of a pair carries no queries)
+        uint64_t* dst = p.parts + (size_t(vslab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
+        for (int c = 0; c < p.kk; ++c) dst[c] = lds_u64(mylist + c * LSTRIDE);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // nobody leaves while the peer may still touch its barriers / TMEM
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
+                   : "memory");
   }
 }
 
@@ -530,8 +660,15 @@ static EncodeTiledFn encode_tiled() {
 
 struct Plan {
   int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups, nbox;
+  bool pair;   // CTA pairs (cta_group::2): two query blocks share every MMA
   size_t smem;
 };
+
+// CTA pairs are opt-in for now (DRS_UMMA_PAIR=1)
+static bool pair_enabled() {
+  static const int on = [] { const char* e = getenv("DRS_UMMA_PAIR"); return e ? atoi(e) : 0; }();
+  return on != 0;
+}
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
   if (dim % MIN_STAGE_K != 0 || dim <= 0 || dim > MAX_D) return false;
@@ -543,19 +680,33 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
     fixed -= size_t(kk) * BLOCK_M * 8;
     pl.n_groups = 1;
   }
-  // 32 KB stages (K = 256) when the dimension allows and at least three of them fit; else 16 KB stages
-  pl.nbox = (dim % 256 == 0 && fixed + 3 * size_t(4 * BOX_BYTES) <= SMEM_LIMIT) ? 4 : 2;
-  const size_t STAGE_BYTES = size_t(pl.nbox) * BOX_BYTES;
-  if (fixed + size_t(pl.nbox == 4 ? 3 : MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
+  const int g = sm_count();
+  pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
+  pl.pair = pair_enabled() && pl.nqb >= 2 && (g % 2) == 0 && dim % 256 == 0 && (pl.nqb + 1) / 2 <= g / 2;
+  // 32 KB stages (K = 256) when the dimension allows and at least three of them fit; else 16 KB stages.  In a pair
+  // every CTA holds half of each tile: K = 256 stages of 16 KB.
+  pl.nbox = (dim % 256 == 0 && (pl.pair || fixed + 3 * size_t(4 * BOX_BYTES) <= SMEM_LIMIT)) ? 4 : 2;
+  const size_t STAGE_BYTES = size_t(pl.nbox) * (pl.pair ? BOX_BYTES / 2 : BOX_BYTES);
+  if (fixed + size_t(pl.nbox == 4 && !pl.pair ? 3 : MIN_STAGES) * STAGE_BYTES > SMEM_LIMIT) return false;
   int ns = int((SMEM_LIMIT - fixed) / STAGE_BYTES);
-  if (ns > 24 / pl.nbox) ns = 24 / pl.nbox;
+  if (ns > (pl.pair ? 48 : 24) / pl.nbox) ns = (pl.pair ? 48 : 24) / pl.nbox;
   static const int cap_stages = [] { const char* e = getenv("DRS_UMMA_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
   if (cap_stages > 0 && ns > cap_stages) ns = cap_stages;
   pl.n_stages = ns;
   pl.smem = fixed + size_t(ns) * STAGE_BYTES;
-  pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
   pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
-  const int g = sm_count();
+  if (pl.pair) {
+    // one item per CTA pair: (pair of query blocks, slab)
+    const int nqb2 = (pl.nqb + 1) / 2, gp = g / 2;
+    int s = gp / nqb2;
+    if (s > pl.n_tiles) s = pl.n_tiles;
+    pl.n_slabs = s < 1 ? 1 : s;
+    const int items = nqb2 * pl.n_slabs;
+    pl.grid = 2 * (items < gp ? items : gp);
+    const int m = (kk + pl.n_groups * pl.n_slabs - 1) / (pl.n_groups * pl.n_slabs);
+    pl.m_rank = (items <= gp && m <= 4) ? m : 0;
+    return true;
+  }
   // One item per CTA whenever the query blocks fit: every slab of a query block is then resident at
   // the same time, which the pooled threshold relies on (and no CTA reloads its A operand).
   int s = pl.nqb <= g ? g / pl.nqb : 1;
@@ -595,7 +746,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(n_rows)};
   const cuuint64_t gstride[1] = {cuuint64_t(dim) * 2};
-  const cuuint32_t box[2] = {BOX_K, TILE_N};
+  const cuuint32_t box[2] = {BOX_K, cuuint32_t(pl.pair ? TILE_N / 2 : TILE_N)};   // a CTA of a pair loads half a tile
   const cuuint32_t estride[2] = {1, 1};
   CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d_corpus), gdim, gstride, box, estride,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -622,12 +773,28 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   const char* dbg = getenv("DRS_UMMA_DEBUG");
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
   DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
-  if (pl.nbox == 4) {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    dense_umma_kernel<4><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+  if (pl.pair) {
+    auto kern = dense_umma_kernel<4, true>;
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+  } else if (pl.nbox == 4) {
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<4, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   } else {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    dense_umma_kernel<2><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<2, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   }
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
