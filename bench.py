@@ -342,7 +342,7 @@ def run_ours(args):
     d_ms, d_n = prof["dense_select"]
     flops = 2.0 * args.queries * n_local * EMB_DIM
     dense_tflops = flops / (d_ms / max(d_n, 1) / 1e3) / 1e12 if d_ms > 0 else 0.0
-    traffic, traffic_bm25 = None, None
+    traffic, traffic_bm25, l2sm_bm25, issue_bm25 = None, None, None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
@@ -351,6 +351,8 @@ def run_ours(args):
         if world == 1 and all(wl.get(k) == getattr(args, k) for k in ("chunks", "queries", "top_k", "fusion", "vocab")):
             traffic = tj.get("dense_select_bytes_per_launch")
             traffic_bm25 = tj.get("bm25_select_bytes_per_launch")
+            l2sm_bm25 = tj.get("bm25_select_l2_to_sm_bytes_per_launch")
+            issue_bm25 = tj.get("bm25_select_issue_active_pct")
     except Exception:
         pass
     roofline_dense = {"kernel": "dense_umma_kernel" if _lib.load().drs_dense_last_kernel() == 2 else "dense_simt_kernel",
@@ -367,6 +369,8 @@ def run_ours(args):
                      "peak_source": peaks["source"], "bytes_per_launch": bm_bytes,
                      "sum_df_per_batch": sum_df, "ms_per_launch": b_ms / max(b_n, 1),
                      "dram_gbs": (traffic_bm25 / (b_ms / max(b_n, 1) / 1e3) / 1e9) if (traffic_bm25 and b_ms > 0) else None,
+                     "l2_to_sm_gbs": (l2sm_bm25 / (b_ms / max(b_n, 1) / 1e3) / 1e9) if (l2sm_bm25 and b_ms > 0) else None,
+                     "issue_active_pct_ncu": issue_bm25,
                      "note": "algorithmic bytes = 8 B per posting visited (SURVEY 8d); head terms are read from packed "
                              "2-byte dense rows and queries share rows/postings through L2, so real DRAM traffic "
                              "(`traffic`) is far below the algorithmic figure and frac can exceed 1: the kernel is "
