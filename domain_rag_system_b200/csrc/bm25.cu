@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
   __shared__ int s_slot[BM25_TCHUNK];                        // dense row of the staged term, or -1
   __shared__ int s_drow[BM25_TCHUNK];                        // compacted dense rows, query order
   __shared__ int s_nd;
+  __shared__ const uint16_t* s_rowp[BM25_TCHUNK];   // start of the compacted dense rows
   __shared__ int s_term[BM25_TCHUNK];
   __shared__ long long s_base[BM25_TCHUNK];
 
@@ -164,7 +165,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         const int i = b0 + tid;
         const bool f = i < nstaged && s_slot[i] >= 0;
         const unsigned m = __ballot_sync(0xffffffffu, f);
-        if (f) s_drow[nd + __popc(m & ((1u << tid) - 1u))] = s_slot[i];
+        if (f) {
+          const int at = nd + __popc(m & ((1u << tid) - 1u));
+          s_drow[at] = s_slot[i];
+          s_rowp[at] = ix.d_dense_impact + size_t(s_slot[i]) * ix.dense_stride;
+        }
         nd += __popc(m);
       }
       if (tid == 0) s_nd = nd;
@@ -254,11 +259,12 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         const int dk = ix.dense_shift - sh;   // row value -> score units: << dk (>> -dk when negative)
         auto unpack_add = [&](int4& lo4, int4& hi4, const uint4 w, int i) {
           int4 cl, ch;   // this sweep's contribution to my eight documents
-          if (dk >= 0) {
-            cl.x = int((w.x & 0xffffu) << dk); cl.y = int((w.x >> 16) << dk);
-            cl.z = int((w.y & 0xffffu) << dk); cl.w = int((w.y >> 16) << dk);
-            ch.x = int((w.z & 0xffffu) << dk); ch.y = int((w.z >> 16) << dk);
-            ch.z = int((w.w & 0xffffu) << dk); ch.w = int((w.w >> 16) << dk);
+          if (dk >= 0) {   // value * 2^dk: the multiply folds into the add below (one IMAD per document)
+            const int sc2 = 1 << dk;
+            cl.x = int(w.x & 0xffffu) * sc2; cl.y = int(w.x >> 16) * sc2;
+            cl.z = int(w.y & 0xffffu) * sc2; cl.w = int(w.y >> 16) * sc2;
+            ch.x = int(w.z & 0xffffu) * sc2; ch.y = int(w.z >> 16) * sc2;
+            ch.z = int(w.w & 0xffffu) * sc2; ch.w = int(w.w >> 16) * sc2;
           } else {
             cl.x = int((w.x & 0xffffu) >> -dk); cl.y = int((w.x >> 16) >> -dk);
             cl.z = int((w.y & 0xffffu) >> -dk); cl.w = int((w.y >> 16) >> -dk);
@@ -277,10 +283,10 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         };
         for (int g0 = 0; g0 < nd; g0 += 4) {
           const int ng = min(4, nd - g0);
-          const uint4* r0 = reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0]) * ix.dense_stride + doc0);
-          const uint4* r1 = ng > 1 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 1]) * ix.dense_stride + doc0) : r0;
-          const uint4* r2 = ng > 2 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 2]) * ix.dense_stride + doc0) : r0;
-          const uint4* r3 = ng > 3 ? reinterpret_cast<const uint4*>(ix.d_dense_impact + size_t(s_drow[g0 + 3]) * ix.dense_stride + doc0) : r0;
+          const uint4* r0 = reinterpret_cast<const uint4*>(s_rowp[g0] + doc0);
+          const uint4* r1 = ng > 1 ? reinterpret_cast<const uint4*>(s_rowp[g0 + 1] + doc0) : r0;
+          const uint4* r2 = ng > 2 ? reinterpret_cast<const uint4*>(s_rowp[g0 + 2] + doc0) : r0;
+          const uint4* r3 = ng > 3 ? reinterpret_cast<const uint4*>(s_rowp[g0 + 3] + doc0) : r0;
           const uint4 zu = make_uint4(0, 0, 0, 0);
           const int4 z = make_int4(0, 0, 0, 0);
           for (int i = tid; i < T8; i += 2 * BM25_THREADS) {
