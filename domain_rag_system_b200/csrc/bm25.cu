@@ -1,32 +1,34 @@
 // BM25 over a term-major CSR inverted index, document-partitioned into tiles of 8192 documents.
 //
-// Stage 1 (bm25_select).  A CTA owns a run of consecutive tiles (an x-slice) and walks ALL of them for one
-// query before taking its next query (grid.y strides over the queries), so its threshold is warm after the
-// first tile.  Per (tile, query):
-//   * pass A -- the query's head terms (df >= N/4, ~80 % of a Zipfian query's postings) are added from
-//     DENSE per-document impact rows, up to four rows fused per sweep (16-byte loads, no scatter); the
-//     first sweep also initialises the shared-memory fp32 score tile;
-//   * pass B -- every other term streams the slice of its postings inside the tile (16-byte loads of doc
-//     ids and fp32 impacts, 8 bytes per posting), one term per barrier: a term never repeats a document,
-//     so its read-modify-writes need no atomics, and the next term's first loads are issued before the
-//     barrier;
-//   * scan -- highest document first, four documents per 16-byte shared load, against a 64-bit
-//     (score, doc) threshold; survivors go to an append area and are merged into the CTA's top-kk by a
-//     block bitonic sort when enough pile up.  Scan steps grow geometrically while the list is young so
-//     the early sorts stay small; a global per-query threshold (atomicMax) lets CTAs prune each other.
-// Term metadata is staged once per (CTA, query).
-// Additions into a document's score always happen in the same order (head terms in query order, then
-// the other terms in query order), so documents with identical (term, impact) patterns get identical
-// fp32 sums: the reference's exact fp64 ties survive this fp32 pre-selection.  Tiles and documents are
-// visited in DESCENDING order so that, among equal scores, the larger document id (which the tie rule
-// prefers) is seen first and later equal scores are rejected.
-// The kernel's algorithmic traffic is 8 bytes per posting visited; measured DRAM traffic is ~10x lower
-// (queries share head-term rows through L2), so its practical bound is shared-memory read-modify-writes
-// and the ~7 us of barriers and dependent loads every (tile, query) pair pays.
+// Stage 1 (bm25_select_kernel<false>): INTEGER pre-selection.  Impacts are stored in fixed point
+// (round(impact * 2^s), |.| <= 2^26), so a document's pre-selection score is an integer sum: the order of the
+// additions is free (shared-memory atomics, no barrier between terms) and documents with the same
+// (term, impact) multiset tie exactly, as they do in the reference's fp64 arithmetic.
+//   * work item = (slice of <= 32 consecutive tiles, query); persistent CTAs pull items from one atomic counter
+//     in SLICE-MAJOR order, so the whole grid works on one slice at a time and that slice's rows and postings
+//     stay in L2 while every query passes over them;
+//   * per (tile, query), on an int32 score tile in shared memory:
+//       pass A -- the query's head terms (df >= N/4: ~94 % of a Zipfian query's postings) are added from dense
+//                 rows of packed 14-bit values (16-byte loads = 8 documents, four rows summed as packed 16-bit
+//                 lanes), by the thread that owns the documents; the first sweep also initialises the tile;
+//       pass B -- the other terms' postings inside the tile are cut into chunks of 128 (aligned 16-byte loads of
+//                 doc ids and impacts), the warps take chunks round-robin with the next chunk's loads in flight,
+//                 and add with shared-memory integer atomics;
+//       selection -- with a warm positive threshold and no negative impacts, sums only grow: the thread that
+//                 takes a document across the threshold (old < tau <= new) notes it, and the tile is never
+//                 scanned.  Otherwise (cold list, negative-idf corpora): a vectorised scan, highest document
+//                 first, with geometric steps while the list is young and a segment-wise overflow path;
+//       merge  -- survivors + list <= 256 keys: rank by counting (keys are distinct); else a block bitonic sort.
+//                 A global per-query threshold (atomicMax) lets the CTAs prune each other.
+// Stage 2 (bm25_rescore_kernel): the kk candidates per query are re-scored in fp64 with rank_bm25's exact
+// operation order (one thread per (candidate, token) looks the posting up by binary search), ranked by
+// (score desc, doc desc), and the selection is PROVEN with an error bound or flagged.
+// Stage 3 (bm25_select_kernel<true>, predicated on the flags): every document that can still belong to the
+// top-k' of a flagged query is re-scored exactly; exact (score, doc) top-k' per slice, merged by merge_pairs.
 //
-// Stage 2 (bm25_rescore): the kk surviving candidates per query are re-scored in fp64 with
-// rank_bm25's exact operation order (tf looked up by binary search), sorted by
-// (score desc, doc desc), and the first k' are emitted.
+// The kernel's algorithmic traffic is 8 bytes per posting visited; real DRAM traffic is ~100x lower
+// (2-byte head-term rows shared by all queries through L2), so its practical bound is issue slots, shared-memory
+// atomics and the per-phase latency of every (tile, query) pair, not HBM.
 #include <climits>
 
 #include "common.cuh"

@@ -170,3 +170,34 @@ def test_load_reference_style_bm25_pickle_without_rank_bm25(tmp_path):
     bj = BM25Indexer(device="cpu")
     bj.load(str(tmp_path / "ours.pkl"))
     assert bj.bm25.avgdl == bi.bm25.avgdl and torch.equal(bj.bm25.t["post_doc"], bi.bm25.t["post_doc"])
+
+
+def test_bm25_struct_layout_matches_the_header(tmp_path):
+    """ctypes mirrors `drs_bm25_index` by hand; a field added on one side only (or assigned under a stale name:
+    ctypes silently accepts unknown attributes) shifts every pointer after it.  gcc is the referee."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    fields = [f[0] for f in _lib.Bm25IndexStruct._fields_]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    body = "\n".join(f'  printf("{f} %zu\\n", offsetof(drs_bm25_index, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "drs_b200.h"\nint main(void) {\n' + body +
+                   '\n  printf("sizeof %zu\\n", sizeof(drs_bm25_index));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.Bm25IndexStruct, f).offset, f
+    assert int(out["sizeof"]) == ctypes.sizeof(_lib.Bm25IndexStruct)
+    # every header field is mirrored (the C program above would not compile for a field unknown to the header)
+    hdr = open(os.path.join(root, "include", "drs_b200.h")).read()
+    struct_body = hdr[hdr.index("typedef struct drs_bm25_index {"):hdr.index("} drs_bm25_index;")]
+    struct_body = re.sub(r"/\*.*?\*/", "", struct_body, flags=re.S)
+    names = re.findall(r"(\w+)\s*;", struct_body)
+    assert names == fields
+    # and struct() fills every one of them from the index (no stale attribute names)
+    offs, toks = synth.zipf_docs(300, vocab=40, seed=1, len_min=2, len_max=20)
+    st = Bm25DeviceIndex.from_token_ids(offs, toks, 40, device="cpu", tile_docs=256).struct()
+    assert not (set(vars(st)) - set(fields)), "attribute assigned that is not a struct field"
