@@ -45,8 +45,9 @@ class VectorIndexer:
             self.storage_path = None
         metric = distance_metric.lower()
         self.distance_metric = metric if metric in ("cosine", "euclidean", "dot") else "cosine"
-        if self.distance_metric != "cosine":
-            raise NotImplementedError("only distance_metric='cosine' is built (SURVEY.md 8f row 3)")
+        if self.distance_metric == "euclidean":
+            raise NotImplementedError("distance_metric='euclidean' is not built (SURVEY.md 8f row 3)")
+        self._row_scale = 1.0                        # 'dot': largest row norm R (rows are ranked by q.c / R)
         self.device = torch.device(device) if device is not None else torch.device("cuda")
         self.rows: torch.Tensor | None = None        # bf16 [N, D] in HBM
         self.inv_norm: torch.Tensor | None = None    # fp32 [N]
@@ -109,6 +110,15 @@ class VectorIndexer:
             t = t.to(torch.bfloat16)
         self.rows = t.contiguous()
         self.inv_norm = _lib.row_inv_norms(self.rows)
+        if self.distance_metric == "dot":
+            # Distance.DOT (vector_indexer.py:57-62): rows and query are NOT normalised, score = q . c.
+            # The kernels scale every row by inv_norm[row] and need |c| * inv_norm <= 1 for their exactness
+            # bound, so all rows get the same factor 1/R (R = largest row norm): the ranking is the dot
+            # product's, and topk_vectors() multiplies the scores back by R * |q|.
+            nz = self.inv_norm > 0
+            r = float((1.0 / self.inv_norm[nz]).max()) if bool(nz.any()) else 1.0
+            self._row_scale = r
+            self.inv_norm = torch.full_like(self.inv_norm, 1.0 / r)
         self._mask_cache.clear()
         self._text_rows = None
 
@@ -150,8 +160,11 @@ class VectorIndexer:
     # -- batched device API (additive) ---------------------------------------------------------
     def topk_vectors(self, q_f32: torch.Tensor, kprime: int, row_mask=None, kernel=_lib.DENSE_AUTO):
         """fp32 device queries [Q, D] -> (scores fp32 [Q,k'], ids int64 [Q,k'], flags int32 [Q])."""
-        return _lib.dense_topk(q_f32, self.rows, self.inv_norm, kprime, row_mask=row_mask, kernel=kernel,
-                               ws=self._ws)
+        scores, ids, flags = _lib.dense_topk(q_f32, self.rows, self.inv_norm, kprime, row_mask=row_mask,
+                                             kernel=kernel, ws=self._ws)
+        if self.distance_metric == "dot":
+            scores = scores * (torch.linalg.vector_norm(q_f32, dim=1, keepdim=True) * self._row_scale)
+        return scores, ids, flags
 
     # -- vector_indexer.py:165-230 ---------------------------------------------------------------
     def search(self, query: str, top_k: int = 10, filters: Dict = None, score_threshold: float = None) -> List[Dict]:

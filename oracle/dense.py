@@ -49,6 +49,13 @@ def cosine_scores(rows_normed: np.ndarray, query, exact_rows: bool = False,
     return out
 
 
+def dot_scores(rows: np.ndarray, query) -> np.ndarray:
+    """``Distance.DOT`` (``vector_indexer.py:57-62``): nothing is normalised, score = row . query.
+    fp64 [N]; ``rows`` are the stored vectors as the index holds them (here: the bf16 values widened)."""
+    q = np.array(list(np.asarray(query).tolist()), dtype=np.float64)
+    return np.ascontiguousarray(rows, dtype=np.float32).astype(np.float64) @ q
+
+
 def cosine_scores_batch(rows_normed: np.ndarray, queries: np.ndarray, block: int = 1 << 15) -> np.ndarray:
     """fp64 [Q, N] scores for a batch (BLAS dgemm per block)."""
     q = np.asarray(queries, dtype=np.float64)

@@ -378,6 +378,31 @@ def test_dropin_pipeline_matches_reference_golden(tmp_path):
     assert exact >= len(g["cases"]) // 3
 
 
+def test_dropin_dot_metric_matches_oracle():
+    """distance_metric='dot': un-normalised rows of very different lengths, un-normalised queries."""
+    from domain_rag_system_b200.indexing.vector_indexer import VectorIndexer
+    rng = np.random.default_rng(5)
+    n, d = 6000, 768
+    rows = rng.standard_normal((n, d)).astype(np.float32) * rng.uniform(0.05, 4.0, size=(n, 1)).astype(np.float32)
+    rows[17] = 0.0
+    emb = TableEmbedder(dim=d)
+    vi = VectorIndexer(embedder=emb, use_in_memory=True, distance_metric="dot", device=DEV)
+    vi.create_collection()
+    vi.set_rows(torch.from_numpy(rows))
+    stored = vi.rows.float().cpu().numpy()                      # what the index holds (bf16 values)
+    q = (rng.standard_normal((5, d)) * rng.uniform(0.5, 3.0, size=(5, 1))).astype(np.float32)
+    for kernel in (_lib.DENSE_SIMT, _lib.DENSE_UMMA):
+        sc, ids, flags = vi.topk_vectors(torch.from_numpy(q).to(DEV), 10, kernel=kernel)
+        sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+        for i in range(q.shape[0]):
+            full = odense.dot_scores(stored, q[i])
+            want, _ = odense.dense_search(full, 10)
+            assert np.array_equal(ids[i], want), f"dot q{i}: ids differ"
+            assert np.allclose(sc[i], full[want], rtol=1e-3, atol=1e-5)     # north-star tolerance for scores
+    with pytest.raises(NotImplementedError):
+        VectorIndexer(embedder=emb, use_in_memory=True, distance_metric="euclidean", device=DEV)
+
+
 def test_dropin_error_behaviour(tmp_path):
     bi = BM25Indexer()
     with pytest.raises(ValueError, match="Index not built"):
