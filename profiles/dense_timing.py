@@ -1,3 +1,7 @@
+"""Times drs_dense_topk's selection kernel alone (1 M x 768, 1000 queries) -- the driver of the timing experiments
+in DESIGN.md 4.1:   DRS_UMMA_DEBUG=<bits> [DRS_UMMA_STAGES=n] [DRS_UMMA_PAIR=1] [KP=k'] python profiles/dense_timing.py
+bits: 2 no heap inserts, 4 half of every TMA stage, 8 every other MMA, 16 no pass 1, 32 no accumulator read,
+64 / 128 MMA N = 32 / 128, 256 alternate accumulators.  Results are garbage with any bit set; only the clock matters."""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from domain_rag_system_b200 import _lib, synth
