@@ -13,8 +13,9 @@
 //                them by inv_norm[row] and compares against its private threshold (the kk-th best so
 //                far); the rare survivors replace the minimum of a private list in shared memory.
 //
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM allocator,
-// warps 4..7 = A loader + epilogue.  Work item = (block of 128 queries, slab of corpus tiles);
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; optionally warps 3 and 2 as well: ring stages
+// dealt round-robin, every MMA accumulates, the epilogue zeroes the accumulator it drained), warp 2 = TMEM allocator,
+// warps 4..11 = A loader + two epilogue groups.  Work item = (block of 128 queries, slab of corpus tiles);
 // items are dealt round-robin so CTAs that run concurrently share corpus tiles through L2.
 // Output: one partial list of kk keys per (slab, query); merged and exactly re-scored downstream.
 #include <cuda.h>
@@ -57,6 +58,7 @@ struct Params {
   uint32_t debug;
   int m_rank;      // ceil(kk / (n_groups*n_slabs)) if <= 4 and all slabs run concurrently, else 0 (pooling off)
   int n_groups;    // epilogue warp groups (candidate heaps per query per CTA): 2, or 1 for large kk
+  int n_issuers;   // warps issuing MMAs (1..3): ring stages are dealt round-robin among them
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -270,7 +272,9 @@ __device__ __forceinline__ uint64_t heap_replace_root(uint32_t lst, int kk, uint
 // its tensor memory and HALF of every 64-row corpus tile in its shared memory; the leader CTA issues M = 256 MMAs
 // whose accumulator rows 0..127 land in the leader's TMEM and 128..255 in the peer's.  The fixed per-MMA cost is
 // paid once for two query blocks and every shared-memory byte feeds twice the math.
-template <int NBOX, bool PAIR>
+// MULTI = several MMA-issuing warps (p.n_issuers = 2 or 3); a template parameter so that the single-issuer loop
+// keeps its handful of instructions per MMA.
+template <int NBOX, bool PAIR, bool MULTI>
 __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_constant__ CUtensorMap tmap, Params p) {
   constexpr int STAGE_K = NBOX * BOX_K;
   constexpr int BOXB = PAIR ? BOX_BYTES / 2 : BOX_BYTES;   // a box is 64 K-elements x 64 (32 in a pair) rows
@@ -305,8 +309,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
       mbar_init(full + s, PAIR ? 2 : 1);
       mbar_init(empty + s, 1);
     }
-    mbar_init(tfull + 0, 1);
-    mbar_init(tfull + 1, 1);
+    mbar_init(tfull + 0, MULTI ? p.n_issuers : 1);   // every issuing warp commits the accumulator once per tile
+    mbar_init(tfull + 1, MULTI ? p.n_issuers : 1);
     mbar_init(tempty + 0, PAIR ? 8 : 4);
     mbar_init(tempty + 1, PAIR ? 8 : 4);
     mbar_init(a_ready, (PAIR ? 8 : 4) * p.n_groups);
@@ -373,13 +377,21 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1 && rank == 0) {
+  } else if (rank == 0 && (warp == 1 || (MULTI && (warp == 3 || (warp == 2 && p.n_issuers > 2))))) {
     // ===================================================================== MMA issuer (the leader CTA of a pair)
     // The WHOLE warp walks the loops (so every address below is warp-uniform and lives in uniform
     // registers); one elected lane issues the tcgen05 instructions.  A tile's 48 MMAs take 32 tensor
     // cycles each, so the issue path must stay within a handful of instructions per MMA.
     uint32_t st = 0, it = 0, item_idx = 0;
     uint32_t s = 0, ph = 0;   // ring slot / phase, stepped without divisions
+    // Several issuing warps (1, 3, 2): a tcgen05.mma with A in tensor memory costs ~26 cycles on top of its 32
+    // tensor cycles when one thread issues them back to back; issued from different warps the fixed parts overlap.
+    // The ring stages are dealt round-robin.  Because the stages of one tile are then issued in no particular
+    // order, no MMA may be "the first" (overwrite): every MMA accumulates, and the epilogue zeroes an accumulator
+    // after reading it.
+    constexpr bool dual = MULTI;
+    const uint32_t me = warp == 1 ? 0u : (warp == 3 ? 1u : 2u);
+    const uint32_t n_iss = MULTI ? uint32_t(p.n_issuers) : 1u;
     constexpr uint32_t IDESC_PAIR = (IDESC & ~(0x1fu << 24)) | (uint32_t((2 * BLOCK_M) >> 4) << 24);   // M = 256
     for (int item = cta; item < n_items; item += n_ctas, ++item_idx) {
       int t0, t1;
@@ -394,10 +406,13 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ACC_COL0 + as * TILE_N;
         for (int ks = 0; ks < kst; ++ks, ++st) {
-          if constexpr (PAIR) mbar_wait_cluster(full + s, ph, 4);
-          else mbar_wait(full + s, ph, 4);
-          tc_fence_after();
-          if (elect_one()) {
+          const bool mine = !dual || (st % n_iss) == me;
+          if (mine) {
+            if constexpr (PAIR) mbar_wait_cluster(full + s, ph, 4);
+            else mbar_wait(full + s, ph, 4);
+            tc_fence_after();
+          }
+          if (mine && elect_one()) {
             const uint64_t desc0 = make_b_desc(smem_u32(ring + size_t(s) * STAGE_BYTES));
             const uint32_t a0 = tmem_base + uint32_t(ks) * (STAGE_K / 2);
 #pragma unroll
@@ -414,7 +429,8 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
               if constexpr (PAIR) {
                 umma_ts_pair(d_tmem, a0 + k16 * 8, b_desc, IDESC_PAIR, (ks | k16) != 0 ? 1u : 0u);
               } else {
-                if (!(p.debug & 8) || (k16 & 1) == 0) umma_ts(dd, a0 + k16 * 8, b_desc, idesc, (ks | k16) != 0 ? 1u : 0u);
+                if (!(p.debug & 8) || (k16 & 1) == 0)
+                  umma_ts(dd, a0 + k16 * 8, b_desc, idesc, (dual || (ks | k16) != 0) ? 1u : 0u);
               }
             }
             if constexpr (PAIR) {
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
               if (ks == kst - 1) tc_commit_pair(tfull + as);  // both CTAs' halves of the accumulator are complete
             } else {
               tc_commit(empty + s);                      // the stage is free once these MMAs have read it
-              if (ks == kst - 1) tc_commit(tfull + as);  // accumulator tile complete
+              if (ks == kst - 1 && !dual) tc_commit(tfull + as);  // accumulator tile complete
             }
           }
           __syncwarp();
@@ -430,6 +446,10 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
             s = 0;
             ph ^= 1;
           }
+        }
+        if (dual) {
+          if (elect_one()) tc_commit(tfull + as);
+          __syncwarp();
         }
       }
     }
@@ -448,6 +468,19 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
     uint32_t it = 0;                         // tiles issued so far (both groups), mirrors the MMA warp
     const uint32_t a_ready_leader = PAIR ? mapa_u32(smem_u32(a_ready), 0) : 0u;
     const uint32_t tempty_leader = PAIR ? mapa_u32(smem_u32(tempty), 0) : 0u;
+    // several issuing warps => every MMA accumulates: the accumulators start at zero and are zeroed again by the
+    // epilogue that drained them (group g owns stage g; a single group owns both)
+    constexpr bool zacc = MULTI;
+    if (zacc) {
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      for (int stg = (ng == 2 ? grp : 0); stg < (ng == 2 ? grp + 1 : 2); ++stg) {
+        tmem_st32(tmem_base + lane_addr + ACC_COL0 + stg * TILE_N, z);
+        tmem_st32(tmem_base + lane_addr + ACC_COL0 + stg * TILE_N + 32, z);
+      }
+      // (the wait::st + fence before the first a_ready arrival below covers these stores)
+    }
     for (int item = cta; item < n_items; item += n_ctas) {
       const int qb = PAIR ? 2 * (item % nqbx) + int(rank) : item % nqbx, slab = item / nqbx;
       int t0, t1;
@@ -606,6 +639,14 @@ __global__ void __launch_bounds__(THREADS, 1) dense_umma_kernel(const __grid_con
             ++nst;
           }
         }
+        if (zacc) {   // hand the accumulator back zeroed
+          uint32_t z[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) z[j] = 0u;
+          tmem_st32(taddr, z);
+          tmem_st32(taddr + 32, z);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {                          // accumulator stage may be overwritten
@@ -761,6 +802,13 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.gslab = d_gtau + q_stride;
   p.m_rank = pl.m_rank;
   p.n_groups = pl.n_groups;
+  // Three issuing warps by default (DRS_UMMA_ISSUERS overrides): 1.54 -> 1.44 ms at 1 M x 1000 queries, 17.2 -> 14.6 ms
+  // on a 12.5 M-row shard, parity-green.  Only with 32 KB ring stages and two epilogue groups: in the other class
+  // (16 KB stages, one group: k' >= ~60) three issuers faulted on a 10 M-row single-query run for a reason not yet
+  // understood, so that class keeps one issuing warp.
+  static const int n_iss = [] { const char* e = getenv("DRS_UMMA_ISSUERS"); return e ? atoi(e) : 3; }();
+  p.n_issuers = n_iss < 1 ? 1 : (n_iss > 3 ? 3 : n_iss);
+  if (pl.pair || pl.nbox != 4 || pl.n_groups != 2) p.n_issuers = 1;   // several issuers: 32 KB stages + two epilogue groups only
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -774,7 +822,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
   DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
   if (pl.pair) {
-    auto kern = dense_umma_kernel<4, true>;
+    auto kern = dense_umma_kernel<4, true, false>;
     DRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
@@ -789,12 +837,15 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmap, p));
+  } else if (pl.nbox == 4 && p.n_issuers > 1) {
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<4, false, true><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   } else if (pl.nbox == 4) {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    dense_umma_kernel<4, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<4, false, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   } else {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    dense_umma_kernel<2, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
+    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    dense_umma_kernel<2, false, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   }
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
