@@ -201,3 +201,27 @@ def test_bm25_struct_layout_matches_the_header(tmp_path):
     offs, toks = synth.zipf_docs(300, vocab=40, seed=1, len_min=2, len_max=20)
     st = Bm25DeviceIndex.from_token_ids(offs, toks, 40, device="cpu", tile_docs=256).struct()
     assert not (set(vars(st)) - set(fields)), "attribute assigned that is not a struct field"
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours) must print ONE JSON line with the
+    contract's keys, on this CPU-only container too (tiny workload so the test stays fast)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--chunks", "20000",
+                          "--queries", "16", "--steps", "1", "--warmup", "1", "--ref-queries-per-step", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "hybrid_topk_queries_per_sec" and d["unit"] == "queries/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
