@@ -700,7 +700,7 @@ static EncodeTiledFn encode_tiled() {
 }
 
 struct Plan {
-  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups, nbox;
+  int nqb, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups, nbox, n_issuers;
   bool pair;   // CTA pairs (cta_group::2): two query blocks share every MMA
   size_t smem;
 };
@@ -733,6 +733,22 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   if (ns > (pl.pair ? 48 : 24) / pl.nbox) ns = (pl.pair ? 48 : 24) / pl.nbox;
   static const int cap_stages = [] { const char* e = getenv("DRS_UMMA_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
   if (cap_stages > 0 && ns > cap_stages) ns = cap_stages;
+  // MMA-issuing warps.  The ring stages are dealt round-robin, and a warp waits only for ITS stages' `full`
+  // barriers -- by phase parity.  That is sound only if a ring slot is always consumed by the same warp
+  // (n_stages % n_issuers == 0): otherwise a warp can reach a slot whose PREVIOUS lap (another warp's stage) has
+  // not even landed yet, the parity test passes on the stale phase, and it issues MMAs on a buffer still being
+  // filled.  (This is what faulted with 3 issuers on a 4-stage ring; it needs TMA completions one stage out of
+  // order, so it only showed on long runs.)  The ring is therefore trimmed to a multiple of the issuer count.
+  // Several issuers are used in the class they were validated in: 32 KB stages, two epilogue groups.
+  static const int want_iss = [] { const char* e = getenv("DRS_UMMA_ISSUERS"); return e ? atoi(e) : 3; }();
+  pl.n_issuers = 1;
+  if (!pl.pair && pl.nbox == 4 && pl.n_groups == 2 && want_iss > 1) {
+    const int ni = want_iss > 3 ? 3 : want_iss;
+    if (ns >= ni) {
+      pl.n_issuers = ni;
+      ns = (ns / ni) * ni;
+    }
+  }
   pl.n_stages = ns;
   pl.smem = fixed + size_t(ns) * STAGE_BYTES;
   pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
@@ -802,13 +818,7 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.gslab = d_gtau + q_stride;
   p.m_rank = pl.m_rank;
   p.n_groups = pl.n_groups;
-  // Three issuing warps by default (DRS_UMMA_ISSUERS overrides): 1.54 -> 1.44 ms at 1 M x 1000 queries, 17.2 -> 14.6 ms
-  // on a 12.5 M-row shard, parity-green.  Only with 32 KB ring stages and two epilogue groups: in the other class
-  // (16 KB stages, one group: k' >= ~60) three issuers faulted on a 10 M-row single-query run for a reason not yet
-  // understood, so that class keeps one issuing warp.
-  static const int n_iss = [] { const char* e = getenv("DRS_UMMA_ISSUERS"); return e ? atoi(e) : 3; }();
-  p.n_issuers = n_iss < 1 ? 1 : (n_iss > 3 ? 3 : n_iss);
-  if (pl.pair || pl.nbox != 4 || pl.n_groups != 2) p.n_issuers = 1;   // several issuers: 32 KB stages + two epilogue groups only
+  p.n_issuers = pl.n_issuers;
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
