@@ -76,6 +76,17 @@ class VectorIndexer:
             with open(d / "payload.pkl", "rb") as f:
                 self.payloads = pickle.load(f)
             self._exists = True
+        elif (d / "storage.sqlite").exists():
+            # a directory written by the reference's qdrant-client local mode (vector_indexer.py:51-53,68):
+            # import its points once, then persist in our own format next to it
+            from .qdrant_import import read_qdrant_local
+            vecs, payloads, _cfg = read_qdrant_local(self.storage_path, self.collection_name)
+            print(f"Importing {len(payloads)} points from the Qdrant local collection at {d}")
+            if len(payloads):
+                self.payloads = payloads
+                self.set_rows(torch.from_numpy(vecs))
+                self._persist()
+            self._exists = True
 
     def _persist(self):
         if self.storage_path is None or self.rows is None:

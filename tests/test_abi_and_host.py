@@ -225,3 +225,91 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert "workload" in d["config"]
+
+
+def _write_qdrant_like_dir(root, name, vectors, payloads, ids, pydantic_v1_state=False):
+    """A local-mode Qdrant directory as qdrant-client >= 1.7 lays it out (restated, see indexing/qdrant_import.py):
+    the points are pickled instances of a class living in `qdrant_client.http.models.models`."""
+    import base64
+    import json
+    import pickle
+    import sqlite3
+    import sys
+    import types
+    mods = ["qdrant_client", "qdrant_client.http", "qdrant_client.http.models", "qdrant_client.http.models.models"]
+    created = [m for m in mods if m not in sys.modules]
+    for m in created:
+        sys.modules[m] = types.ModuleType(m)
+    mod = sys.modules[mods[-1]]
+    try:
+        if pydantic_v1_state:
+            class PointStruct:                                   # pickles with pydantic v1's state layout
+                def __init__(self, **kw):
+                    self.__dict__.update(kw)
+
+                def __getstate__(self):
+                    return {"__dict__": dict(self.__dict__), "__fields_set__": set(self.__dict__),
+                            "__private_attribute_values__": {}}
+        else:
+            import pydantic
+
+            class PointStruct(pydantic.BaseModel):               # a real pydantic (v2) model
+                id: int
+                vector: list
+                payload: dict
+        PointStruct.__module__ = mods[-1]
+        PointStruct.__qualname__ = "PointStruct"
+        mod.PointStruct = PointStruct
+        d = root / "collection" / name
+        d.mkdir(parents=True)
+        con = sqlite3.connect(str(d / "storage.sqlite"))
+        con.execute("CREATE TABLE IF NOT EXISTS points (id TEXT PRIMARY KEY, point BLOB)")
+        for i, v, p in zip(ids, vectors, payloads):
+            key = base64.b64encode(pickle.dumps(i)).decode()
+            con.execute("INSERT INTO points VALUES (?, ?)",
+                        (key, pickle.dumps(PointStruct(id=i, vector=[float(x) for x in v], payload=p))))
+        con.commit()
+        con.close()
+        (root / "meta.json").write_text(json.dumps(
+            {"collections": {name: {"vectors": {"size": len(vectors[0]), "distance": "Cosine"}}}, "aliases": {}}))
+    finally:
+        for m in created:
+            sys.modules.pop(m, None)
+
+
+@pytest.mark.parametrize("v1_state", [False, True])
+def test_qdrant_local_directory_reader(tmp_path, v1_state):
+    """The importer must work WITHOUT qdrant-client (not installed here): stand-in classes take the pickled points'
+    state, rows come back in point-id order whatever the insertion order was."""
+    import sys
+    from domain_rag_system_b200.indexing.qdrant_import import read_qdrant_local
+    rng = np.random.default_rng(3)
+    n, d = 23, 16
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    payloads = [{"chunk_id": f"c{i}", "doc_id": f"d{i // 3}", "source": "s", "chunk_type": "t", "text": f"text {i}",
+                 "metadata": {"k": i}} for i in range(n)]
+    order = rng.permutation(n)                                   # upserts in arbitrary order
+    _write_qdrant_like_dir(tmp_path, "medical_docs", vecs[order], [payloads[i] for i in order],
+                           [int(i) for i in order], pydantic_v1_state=v1_state)
+    assert "qdrant_client" not in sys.modules
+    got, pl, cfg = read_qdrant_local(tmp_path, "medical_docs")
+    assert got.dtype == np.float32 and np.array_equal(got, vecs)
+    assert pl == payloads
+    assert cfg["vectors"]["size"] == d
+    with pytest.raises(FileNotFoundError):
+        read_qdrant_local(tmp_path, "no_such_collection")
+
+
+def test_qdrant_reader_refuses_foreign_classes(tmp_path):
+    import pickle
+    import sqlite3
+    from domain_rag_system_b200.indexing.qdrant_import import read_qdrant_local
+    d = tmp_path / "collection" / "c"
+    d.mkdir(parents=True)
+    con = sqlite3.connect(str(d / "storage.sqlite"))
+    con.execute("CREATE TABLE points (id TEXT PRIMARY KEY, point BLOB)")
+    con.execute("INSERT INTO points VALUES (?, ?)", ("k", pickle.dumps(os.system)))   # a callable from `os`/`posix`
+    con.commit()
+    con.close()
+    with pytest.raises(pickle.UnpicklingError):
+        read_qdrant_local(tmp_path, "c")

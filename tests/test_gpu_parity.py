@@ -487,3 +487,26 @@ def test_bm25_long_queries_shifted_impacts_and_mass_ties():
     queries += [np.array([5, 9, 11], dtype=np.int32)]
     flags = _check_bm25(offs, toks, 300, queries, 10, tile_docs=1024)
     assert (flags == 2).any()                     # 24-fold ties straddle the candidate margin
+
+
+def test_vector_indexer_attaches_to_a_qdrant_local_directory(tmp_path):
+    """storage_path holding the reference's Qdrant local collection (no rows.pt yet): the points are imported on
+    construction, searchable at once, and persisted in our own format for the next start."""
+    from test_abi_and_host import _write_qdrant_like_dir      # tests/ is on sys.path (rootdir conftest)
+    from domain_rag_system_b200.indexing.vector_indexer import VectorIndexer
+    rng = np.random.default_rng(11)
+    n, d = 300, 768
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    texts = [f"chunk number {i}" for i in range(n)]
+    payloads = [{"chunk_id": f"c{i}", "doc_id": f"d{i // 4}", "source": "s", "chunk_type": "t", "text": texts[i],
+                 "metadata": {}} for i in range(n)]
+    _write_qdrant_like_dir(tmp_path, "medical_docs", vecs, payloads, list(range(n)))
+    emb = TableEmbedder(dim=d)
+    emb.add(["probe"], [vecs[42] + 0.01 * rng.standard_normal(d).astype(np.float32)])
+    vi = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
+    assert vi.get_stats()["points_count"] == n
+    hits = vi.search("probe", top_k=3)
+    assert hits[0]["chunk_id"] == "c42" and hits[0]["text"] == texts[42] and hits[0]["score"] > 0.99
+    assert (tmp_path / "collection" / "medical_docs" / "rows.pt").exists()
+    vi2 = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
+    assert [h["chunk_id"] for h in vi2.search("probe", top_k=3)] == [h["chunk_id"] for h in hits]
