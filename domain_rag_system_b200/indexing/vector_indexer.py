@@ -96,7 +96,8 @@ class VectorIndexer:
         torch.save(self.rows.cpu(), d / "rows.pt")
         with open(d / "payload.pkl", "wb") as f:
             pickle.dump(self.payloads, f)
-        with open(self.storage_path / "meta.json", "w") as f:
+        # (not "meta.json": that name belongs to qdrant-client's local mode, whose directory we may be sharing)
+        with open(self.storage_path / "drs_b200_meta.json", "w") as f:
             json.dump({"collections": {self.collection_name: {"size": int(self.rows.shape[1]),
                                                               "distance": self.distance_metric}}}, f)
 

@@ -508,5 +508,6 @@ def test_vector_indexer_attaches_to_a_qdrant_local_directory(tmp_path):
     hits = vi.search("probe", top_k=3)
     assert hits[0]["chunk_id"] == "c42" and hits[0]["text"] == texts[42] and hits[0]["score"] > 0.99
     assert (tmp_path / "collection" / "medical_docs" / "rows.pt").exists()
+    assert "vectors" in (tmp_path / "meta.json").read_text()          # qdrant's own metadata is left alone
     vi2 = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
     assert [h["chunk_id"] for h in vi2.search("probe", top_k=3)] == [h["chunk_id"] for h in hits]
