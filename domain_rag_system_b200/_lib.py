@@ -15,7 +15,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libdrs_b200.so")
 
-DENSE_AUTO, DENSE_SIMT, DENSE_UMMA = 0, 1, 2
+DENSE_AUTO, DENSE_SIMT, DENSE_UMMA, DENSE_UMMA_TS, DENSE_UMMA_PAIR = 0, 1, 2, 3, 4
 MAX_KPRIME, MAX_DIM, MAX_POOL = 128, 1024, 1024
 
 _vp, _i32, _i64, _f64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t

@@ -2,6 +2,8 @@
 // (candidate selection -> k-way merge -> exact re-score -> optional fp32 re-run of unproven queries).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -64,18 +66,40 @@ void prof_end(int kind, cudaStream_t st) {
   ++k.used;
 }
 
+// Which tensor-core kernel serves a shape: the CTA-pair SS-form kernel (dense_pair.cu, M = 256 x N = 256 MMAs) for
+// two or more blocks of 128 queries, the single-CTA kernel with the queries parked in tensor memory (dense_umma.cu)
+// for a single block, 0 = neither.  DRS_TENSOR_KERNEL=ts|pair forces one (A/B measurements).
+enum { TENSOR_NONE = 0, TENSOR_TS = 1, TENSOR_PAIR = 2 };
+static int tensor_variant(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
+  static const int env_forced = [] {
+    const char* e = getenv("DRS_TENSOR_KERNEL");
+    if (!e) return 0;
+    return !strcmp(e, "ts") ? TENSOR_TS : (!strcmp(e, "pair") ? TENSOR_PAIR : 0);
+  }();
+  const bool ts_ok = dense_umma_supported(n_queries, n_rows, dim, kk);
+  const bool pair_ok = dense_pair_supported(n_queries, n_rows, dim, kk);
+  if (kernel == DRS_DENSE_UMMA_TS) return ts_ok ? TENSOR_TS : TENSOR_NONE;
+  if (kernel == DRS_DENSE_UMMA_PAIR) return pair_ok ? TENSOR_PAIR : TENSOR_NONE;
+  const int forced = env_forced;
+  if (forced == TENSOR_TS && ts_ok) return TENSOR_TS;
+  if (forced == TENSOR_PAIR && pair_ok) return TENSOR_PAIR;
+  if (pair_ok && (n_queries > 128 || !ts_ok)) return TENSOR_PAIR;
+  return ts_ok ? TENSOR_TS : (pair_ok ? TENSOR_PAIR : TENSOR_NONE);
+}
+
 static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
-  const bool umma_ok = dense_umma_supported(n_queries, n_rows, dim, kk);
-  if (kernel == DRS_DENSE_UMMA) return umma_ok ? DRS_DENSE_UMMA : -1;
+  const bool umma_ok = tensor_variant(kernel, n_queries, n_rows, dim, kk) != TENSOR_NONE;
+  if (kernel == DRS_DENSE_UMMA || kernel == DRS_DENSE_UMMA_TS || kernel == DRS_DENSE_UMMA_PAIR)
+    return umma_ok ? DRS_DENSE_UMMA : -1;
   if (kernel == DRS_DENSE_SIMT) return DRS_DENSE_SIMT;
   // AUTO: the streaming fp32 kernel reads the corpus once per 4 queries; beyond 8 queries the
-  // tensor-core kernel (one pass per 128 queries) wins.
+  // tensor-core kernels (one pass per 128 / 256 queries) win.
   return (umma_ok && n_queries > 8) ? DRS_DENSE_UMMA : DRS_DENSE_SIMT;
 }
 
 struct DenseWs {
-  size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, total;
-  int simt_parts, umma_parts, umma_qstride;
+  size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, qimg_off, total;
+  int simt_parts, umma_parts, umma_qstride, variant;
 };
 
 static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
@@ -83,7 +107,9 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   const size_t kk = cand_len_umma(kprime);   // the longer of the two candidate lengths sizes every buffer
   const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
   w.simt_parts = dense_simt_grid();
-  w.umma_parts = (which == DRS_DENSE_UMMA) ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0;
+  w.variant = (which == DRS_DENSE_UMMA) ? tensor_variant(kernel, n_queries, n_rows, dim, int(kk)) : TENSOR_NONE;
+  w.umma_parts = w.variant == TENSOR_PAIR ? dense_pair_parts(n_queries, n_rows, dim, int(kk))
+                                          : (w.variant == TENSOR_TS ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0);
   w.umma_qstride = ((n_queries + 127) / 128) * 128;
   const size_t simt_keys = size_t(w.simt_parts) * n_queries * kk;
   const size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk;
@@ -93,7 +119,9 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
                             merge_scratch_keys(w.umma_parts, n_queries, int(kk)));
   w.flags_off = (w.parts_keys + w.cand_keys + w.scratch_keys) * 8;
   w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
-  w.total = w.gtau_off + size_t(w.umma_qstride) * 4 * (1 + size_t(w.umma_parts)) + 256;
+  // bf16 image of the queries (the pair kernel's TMA source), 128-byte aligned
+  w.qimg_off = ((w.gtau_off + size_t(w.umma_qstride) * 4 * (1 + size_t(w.umma_parts)) + 255) / 256) * 256;
+  w.total = w.qimg_off + (w.variant == TENSOR_PAIR ? size_t(dense_pair_query_rows(n_queries)) * dim * 2 : 0) + 256;
   return w;
 }
 
@@ -159,7 +187,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   uint64_t* scratch = w.scratch_keys ? cand + w.cand_keys : nullptr;
   int32_t* flags = d_out_flags ? d_out_flags
                                : reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.flags_off);
-  g_last_dense_kernel = which;
+  g_last_dense_kernel = (which == DRS_DENSE_UMMA && w.variant == TENSOR_PAIR) ? 3 : which;
   int rc;
   if (which == DRS_DENSE_SIMT) {
     {
@@ -176,9 +204,13 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   }
   {
     ProfScope ps(DRS_PROF_DENSE_SELECT, st);
-    rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
-                           w.umma_qstride,
-                           reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off), st);
+    uint32_t* gtau = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off);
+    if (w.variant == TENSOR_PAIR)
+      rc = launch_dense_pair(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                             w.umma_qstride, gtau, reinterpret_cast<uint8_t*>(d_workspace) + w.qimg_off, st);
+    else
+      rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
+                             w.umma_qstride, gtau, st);
   }
   if (rc != DRS_OK) return rc;
   ProfScope pt(DRS_PROF_DENSE_TAIL, st);

@@ -1,0 +1,636 @@
+// Dense cosine candidate selection, CTA-pair form (sm_100a): the main tensor-core kernel.
+//
+//   scores[q, row] = queries[q, :] . corpus[row, :]   as a persistent, warp-specialised bf16 GEMM issued as
+//   tcgen05.mma.cta_group::2 with M = 256 (two blocks of 128 queries, one per CTA of the pair), N = 256 (corpus rows,
+//   128 per CTA) and BOTH operands read from shared memory (SS form).  Every MMA therefore keeps the tensor pipes of
+//   both SMs busy for 128 cycles, which amortises the fixed issue cost that capped the A-in-tensor-memory kernel
+//   (dense_umma.cu, N = 64) at ~55 % pipe occupancy, and each shared-memory byte feeds 256 flop.
+//
+//   operands   = K-chunks of 64 elements of BOTH matrices stream through one TMA ring: per stage and CTA 16 KB of
+//                queries (128 x 64, bf16, pre-converted once per call, L2-resident) + 16 KB of corpus rows
+//                (128 x 64), 128-byte swizzle, `cp.async.bulk.tensor...cta_group::2` signalling the leader's barrier.
+//   D          = 2 x (128 lanes x 256 columns) fp32 in tensor memory: ALL 512 columns, double buffered, so the
+//                epilogue of tile t overlaps the MMAs of tile t+1.
+//   epilogue   = lane L of a CTA is query L of its block; after tcgen05.ld a thread holds its query's 256 scores of the
+//                tile, scales them by inv_norm[row] and compares against its threshold; the rare survivors go to a
+//                thread-private min-heap in shared memory.  Never writes scores.
+//
+// Roles per CTA (384 threads): warp 0 TMA producer (each CTA loads ITS halves), warp 1 MMA issuer (leader CTA only,
+// one elected lane), warp 2 tensor-memory allocator, warps 4..11 two epilogue groups (one group when the heaps of a
+// large k' leave no room for two).  Work item = (pair of query blocks, slab of corpus tiles); the pairs that run
+// concurrently cover the same slab for different query blocks, so the corpus leaves HBM about once.
+// Output: one partial list of kk keys per (virtual slab, query); merged and exactly re-scored downstream (select.cu).
+#include <cuda.h>
+
+#include <cstdio>
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+namespace drs {
+namespace umma {
+namespace ss2 {
+
+constexpr int TILE_N = 256;                          // corpus rows per accumulator tile (128 per CTA)
+constexpr int HALF_N = 128;
+constexpr int STAGE_K = 64;                          // K elements per ring stage: 64 bf16 = one 128-byte swizzle row
+constexpr int A_BYTES = BLOCK_M * STAGE_K * 2;       // 16384: my 128 queries x 64
+constexpr int B_BYTES = HALF_N * STAGE_K * 2;        // 16384: my 128 corpus rows x 64
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 32768 per CTA
+constexpr int THREADS = 384;
+constexpr int MAX_STAGES = 6;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+// D = f32, A = B = bf16, both K-major, N = 256, M = 256 (over the pair)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TILE_N >> 3) << 17) |
+                           (uint32_t((2 * BLOCK_M) >> 4) << 24);
+
+struct Params {
+  const float* inv_norm;
+  const uint8_t* mask;
+  uint64_t* parts;
+  uint32_t* gtau;    // [q_stride] zero-initialised shared thresholds
+  uint32_t* gslab;   // [n_vslabs][q_stride] zero-initialised: each virtual slab's m_rank-th best inserted score
+  int64_t n_rows;
+  int n_queries, nqb, nqb2, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
+  int m_rank;        // ceil(kk / n_vslabs) if <= 6 and every slab of a query block is resident at once, else 0
+  int n_groups;      // epilogue warp groups == candidate heaps per query per CTA
+  uint32_t debug;    // timing experiments only (results are garbage): 1 no inserts, 2 no epilogue work
+  unsigned long long* trace;   // DRS_PAIR_TRACE: per tile of block 0 / warp 4: {clock at accumulator ready, clock at
+                               // tile done, flagged columns}; NULL otherwise
+};
+
+// D[tmem, 256 x 256 over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, 128 rows per CTA]^T
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// fp32 queries -> bf16 [nqb2 * 256, dim], rows beyond n_queries zero (the TMA source of the A operand)
+__global__ void __launch_bounds__(256) queries_to_bf16_kernel(const float* __restrict__ q, int n_queries, int n_pad,
+                                                              int dim, __nv_bfloat16* __restrict__ out) {
+  const int64_t n8 = int64_t(n_pad) * dim / 8;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t e = i * 8;
+    const int row = int(e / dim);
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (row < n_queries) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(q + e));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(q + e + 4));
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+      const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+      w.x = *reinterpret_cast<const uint32_t*>(&p0);
+      w.y = *reinterpret_cast<const uint32_t*>(&p1);
+      w.z = *reinterpret_cast<const uint32_t*>(&p2);
+      w.w = *reinterpret_cast<const uint32_t*>(&p3);
+    }
+    *reinterpret_cast<uint4*>(out + e) = w;
+  }
+}
+
+// Per-lane (= per query) candidate list state.  It lives in local memory (its address is taken by the out-of-line
+// insert below) and is touched only on the rare survivor path; the hot loop carries `tau` in a register.
+struct LaneState {
+  uint64_t root;     // the heap's root = kk-th best candidate once the list is full, 0 before
+  int cnt;           // entries while the list fills by plain appends; == kk once it is a heap
+  float tau_loc;     // score of the root
+  float tm[6];       // this virtual slab's six best inserted scores, descending
+};
+
+// One survivor into a lane's list.  Out of line on purpose: inlined at every call site the heap code made the
+// epilogue loop larger than the instruction cache.  Returns the lane's new local threshold.
+__device__ __noinline__ float lane_insert(LaneState& st, uint32_t mylist, int kk, int m_rank, float s, uint32_t row,
+                                          volatile uint32_t* gs, uint32_t* gt) {
+  const uint64_t key = make_key(s, row);
+  const bool filling = st.cnt < kk;
+  if (!filling && key <= st.root) return st.tau_loc;
+  if (filling) {
+    sts_u64(mylist + st.cnt * LSTRIDE, key);
+    if (++st.cnt == kk) st.root = heap_build(mylist, kk);
+  } else {
+    st.root = heap_replace_root(mylist, kk, key);
+  }
+  if (m_rank > 0 && s > st.tm[5]) {   // keep the six best scores, publish the m-th
+    float a0 = st.tm[0], a1 = st.tm[1], a2 = st.tm[2], a3 = st.tm[3], a4 = st.tm[4], a5 = s;
+    if (a5 > a4) { const float x = a4; a4 = a5; a5 = x; }
+    if (a4 > a3) { const float x = a3; a3 = a4; a4 = x; }
+    if (a3 > a2) { const float x = a2; a2 = a3; a3 = x; }
+    if (a2 > a1) { const float x = a1; a1 = a2; a2 = x; }
+    if (a1 > a0) { const float x = a0; a0 = a1; a1 = x; }
+    st.tm[0] = a0; st.tm[1] = a1; st.tm[2] = a2; st.tm[3] = a3; st.tm[4] = a4; st.tm[5] = a5;
+    const float mth = m_rank == 1 ? a0 : (m_rank == 2 ? a1 : (m_rank == 3 ? a2 : (m_rank == 4 ? a3 : (m_rank == 5 ? a4 : a5))));
+    if (mth > -INFINITY) *gs = ord32(mth);
+  }
+  if (st.root) {
+    st.tau_loc = key_score(st.root);
+    atomicMax(gt, ord32(st.tau_loc));
+  }
+  return st.tau_loc;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, Params p) {
+  const uint32_t rank = cluster_ctarank();            // 0 = leader
+  const int cta = int(blockIdx.x >> 1);               // work-item stream this pair walks
+  const int n_ctas = int(gridDim.x >> 1);
+  extern __shared__ uint8_t smem_dyn[];
+  // carve: [ring | heaps | norm strips | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);
+  float* norm_strips = reinterpret_cast<float*>(lists + size_t(p.n_groups) * p.kk * BLOCK_M);   // [warps][TILE_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_strips + size_t(4 * p.n_groups) * TILE_N);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.n_stages;
+  uint64_t* tfull = bars + 2 * p.n_stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.nqb2 * p.n_slabs;
+  const int kst = p.dim / STAGE_K;   // ring stages per accumulator tile
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_c)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    // The leader's full barriers count the bytes of BOTH CTAs' TMA loads (one arrival: the leader's expect_tx), its
+    // tempty barriers the epilogue warps of both CTAs; empty and tfull are signalled in each CTA by the leader's
+    // multicast commit.
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tfull + 0, 1);
+    mbar_init(tfull + 1, 1);
+    mbar_init(tempty + 0, 8);   // 4 epilogue warps x 2 CTAs
+    mbar_init(tempty + 1, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  auto slab_tiles = [&](int slab, int& t0, int& t1) {
+    t0 = int((int64_t(slab) * p.n_tiles) / p.n_slabs);
+    t1 = int((int64_t(slab + 1) * p.n_tiles) / p.n_slabs);
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    uint32_t s = 0, ph = 0;
+    for (int item = cta; item < n_items; item += n_ctas) {
+      int t0, t1;
+      slab_tiles(item / p.nqb2, t0, t1);
+      const int qrow = (2 * (item % p.nqb2) + int(rank)) * BLOCK_M;   // my block of 128 queries
+      for (int t = t0; t < t1; ++t) {
+        const int crow = t * TILE_N + int(rank) * HALF_N;             // my half of the corpus tile
+        for (int ks = 0; ks < kst; ++ks) {
+          mbar_wait(empty + s, ph ^ 1, 1);
+          if (elect_one()) {
+            uint8_t* dst = ring + size_t(s) * STAGE_BYTES;
+            // My bytes land in MY ring; they are counted by the LEADER's barrier, which expects both CTAs' bytes
+            // with ONE plain local arrival.  (No cluster-scope release here: that costs a MEMBAR.GPU per stage,
+            // which waits for the TMA loads in flight and serialises the ring.)  The peer's bytes may land before
+            // the leader's expect_tx: the transaction count goes negative for a moment, the phase cannot complete
+            // before the leader's arrival.  The peer cannot run a lap ahead: its `empty` barrier is signalled by
+            // MMAs the leader issued after that lap's `full` phase completed.
+            const uint32_t lbar = mapa_u32(smem_u32(full + s), 0);
+            if (rank == 0) mbar_arrive_expect_tx(full + s, 2u * uint32_t(STAGE_BYTES));
+            tma_load_2d_pair(&tmap_q, lbar, dst, ks * STAGE_K, qrow);
+            tma_load_2d_pair(&tmap_c, lbar, dst + A_BYTES, ks * STAGE_K, crow);
+          }
+          __syncwarp();
+          if (++s == uint32_t(p.n_stages)) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================================================================== MMA issuer (leader CTA)
+    // The whole warp walks the loops (addresses stay warp-uniform); one elected lane issues.  A stage is four
+    // M256 x N256 x K16 MMAs of 128 tensor cycles each.
+    uint32_t s = 0, ph = 0, it = 0;
+    for (int item = cta; item < n_items; item += n_ctas) {
+      int t0, t1;
+      slab_tiles(item / p.nqb2, t0, t1);
+      for (int t = t0; t < t1; ++t, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(tempty + as, aph ^ 1, 3);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * TILE_N;
+        for (int ks = 0; ks < kst; ++ks) {
+          mbar_wait(full + s, ph, 4);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t base = smem_u32(ring + size_t(s) * STAGE_BYTES);
+            const uint64_t a0 = make_b_desc(base), b0 = make_b_desc(base + A_BYTES);
+#pragma unroll
+            for (int k16 = 0; k16 < STAGE_K / 16; ++k16)   // +32 bytes per K = 16 step inside the 128-byte swizzle row
+              umma_ss_pair(d_tmem, a0 + uint64_t(k16 * 2), b0 + uint64_t(k16 * 2), IDESC, (ks | k16) != 0 ? 1u : 0u);
+            tc_commit_pair(empty + s);                       // frees the stage in both CTAs
+            if (ks == kst - 1) tc_commit_pair(tfull + as);   // both CTAs' halves of the accumulator are complete
+          }
+          __syncwarp();
+          if (++s == uint32_t(p.n_stages)) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + 4 * p.n_groups) {
+    // ===================================================================== epilogue
+    // Group g owns accumulator stage g and every other tile (two tile-times to drain one tile); a single group
+    // owns both stages.  Each group keeps its own heap per query: a "virtual slab" of the corpus.
+    const int ew = warp & 3;                 // the TMEM sub-partition (lanes 32*ew ..) this warp may touch
+    const int grp = (warp - 4) >> 2;
+    const int L = ew * 32 + lane;            // TMEM lane == query within my block
+    const uint32_t lane_addr = uint32_t(ew * 32) << 16;
+    const int ng = p.n_groups;
+    const uint32_t mylist = smem_u32(lists) + uint32_t(grp * p.kk * BLOCK_M + L) * 8;   // my heap's slot 0
+    float* nstrip = norm_strips + (warp - 4) * TILE_N;
+    const uint32_t tempty_leader = mapa_u32(smem_u32(tempty), 0);
+    const bool no_insert = (p.debug & 1) != 0;
+    uint32_t it = 0;                         // tiles issued so far, mirrors the MMA warp
+    for (int item = cta; item < n_items; item += n_ctas) {
+      const int qb = 2 * (item % p.nqb2) + int(rank), slab = item / p.nqb2;
+      int t0, t1;
+      slab_tiles(slab, t0, t1);
+      const int q = qb * BLOCK_M + L;
+      const bool live = q < p.n_queries;
+      for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
+      // The list fills by plain appends (cnt < kk), is turned into a min-heap once (Floyd), and from then on its
+      // root is the kk-th best candidate: replacing it costs O(log kk).
+      LaneState st;
+      st.root = 0;
+      st.cnt = 0;
+      st.tau_loc = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) st.tm[i] = -INFINITY;
+      // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by every heap working
+      // on q (ordered-u32 image, atomicMax): slabs warm each other's thresholds.  Padding lanes never insert.
+      uint32_t* gt = p.gtau + (live ? q : 0);
+      uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
+      // Pooled threshold: all virtual slabs of a query block run concurrently, each publishes the m-th best score
+      // it has inserted so far in gslab[vslab][q] (m = ceil(kk / #virtual slabs) <= 6).  If every one of them has m
+      // rows scoring >= x, the corpus has >= kk such rows: x = min over virtual slabs is a valid lower bound of the
+      // global kk-th best, and far tighter than any local bound while the lists warm up.
+      const int vslab = slab * ng + grp;
+      volatile uint32_t* gs = p.gslab + size_t(vslab) * p.q_stride + (live ? q : 0);
+      float tau_pool = -INFINITY;
+      float tau_loc = -INFINITY;
+      const int n_vslabs = ng * p.n_slabs;
+      const int pool_every = n_vslabs > 32 ? n_vslabs / 4 : 8;
+      // inverse norms of the tile's 256 rows: lane l fetches rows 8l..8l+7 one tile ahead, parks them in this warp's
+      // strip, and every lane reads all of them by broadcast
+      float4 nA, nB;
+      auto load_norms = [&](int t) {
+        const int64_t r = int64_t(t) * TILE_N + 8 * lane;
+        if (t < t1 && r + 7 < p.n_rows) {
+          nA = __ldg(reinterpret_cast<const float4*>(p.inv_norm + r));
+          nB = __ldg(reinterpret_cast<const float4*>(p.inv_norm + r + 4));
+        } else {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (t < t1 && r + j < p.n_rows) ? __ldg(p.inv_norm + r + j) : 0.f;
+          nA = make_float4(v[0], v[1], v[2], v[3]);
+          nB = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      };
+      const int t_first = (ng == 1) ? t0 : t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of the item
+      load_norms(t_first);
+      int nt = 0;
+      for (int t = t_first; t < t1; t += ng, ++nt) {
+        const uint32_t itt = it + uint32_t(t - t0);      // this tile's global sequence number
+        __syncwarp();                                    // everyone is done reading the previous tile's strip
+        reinterpret_cast<float4*>(nstrip)[2 * lane] = nA;
+        reinterpret_cast<float4*>(nstrip)[2 * lane + 1] = nB;
+        __syncwarp();
+        load_norms(t + ng);                              // prefetch for my next tile
+        // refreshed before each of the first tiles (thresholds move fastest while the heaps fill), then periodically
+        if (live && p.m_rank > 0 && (nt < 8 || (nt % pool_every) == pool_every - 1)) {
+          uint32_t mn = 0xffffffffu;
+          const volatile uint32_t* col = p.gslab + q;
+          for (int sl = 0; sl < n_vslabs; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
+          if (mn != 0u) tau_pool = fmaxf(tau_pool, unord32(mn));   // 0 = some slab has not reported yet
+        }
+        float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
+        if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);   // lands while this tile is processed
+        const uint32_t as = itt & 1u, aph = (itt >> 1) & 1;
+        mbar_wait(tfull + as, aph, 5);
+        tc_fence_after();
+        const uint32_t taddr0 = tmem_base + lane_addr + as * TILE_N;
+        auto insert = [&](float s, int j) {
+          const int64_t row = int64_t(t) * TILE_N + j;
+          if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
+            tau_loc = lane_insert(st, mylist, p.kk, p.m_rank, s, uint32_t(row), gs, gt);
+            tau = fmaxf(tau, tau_loc);
+          }
+        };
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nst = 0;
+        const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && nt < 1000;
+        long long tr0 = 0;
+        int trc = 0;
+        if (tracing) tr0 = clock64();
+        // Survivors of pass 1 are taken out of the REGISTERS the accumulator chunk was loaded into: every lane
+        // that has flagged columns picks ITS OWN lowest one through a select tree, so a round serves up to 32
+        // different columns at once and a chunk costs max-over-lanes(#flagged) rounds, not #distinct columns.
+        // The first four survivors of a tile are only stashed; their heap work runs after the accumulator has
+        // been handed back.
+        auto rounds = [&](uint32_t m, const uint32_t (&acc)[32], int col0) {
+          while (__any_sync(0xffffffffu, m != 0)) {
+            ++trc;
+            if (m != 0) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1;
+              const int jj = col0 + j;
+              const float s = __uint_as_float(pick32(acc, j)) * nstrip[jj];
+              if (nst == 0) { s0 = s; j0 = jj; }
+              else if (nst == 1) { s1 = s; j1 = jj; }
+              else if (nst == 2) { s2 = s; j2 = jj; }
+              else if (nst == 3) { s3 = s; j3 = jj; }
+              else insert(s, jj);                // stash full (warm-up tiles only): insert in place
+              ++nst;
+            }
+          }
+        };
+#pragma unroll 1
+        for (int ch = 0; ch < TILE_N / 64; ++ch) {   // 64 accumulator columns at a time
+          uint32_t acc0[32], acc1[32];
+          const uint32_t taddr = taddr0 + ch * 64;
+          if (!(p.debug & 2)) {
+            tmem_ld32(taddr, acc0);
+            tmem_ld32(taddr + 32, acc1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          if (ch == TILE_N / 64 - 1) {   // the whole tile is in registers (or done): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + as * 8);
+          }
+          if (p.debug & 2) continue;
+          // ---- pass 1, branch-free: which of these 64 scores reach the threshold?
+          uint32_t m0 = 0, m1 = 0;
+          const float4* nb4 = reinterpret_cast<const float4*>(nstrip + ch * 64);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 n = nb4[g];
+            m0 |= (__uint_as_float(acc0[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+            m0 |= (__uint_as_float(acc0[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+            m0 |= (__uint_as_float(acc0[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+            m0 |= (__uint_as_float(acc0[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 n = nb4[8 + g];
+            m1 |= (__uint_as_float(acc1[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+            m1 |= (__uint_as_float(acc1[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+            m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+            m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+          }
+          if (no_insert) m0 = m1 = 0;
+          // ---- pass 2, rare and rolled
+          rounds(m0, acc0, ch * 64);
+          rounds(m1, acc1, ch * 64 + 32);
+        }
+        // ---- the stashed survivors
+        if (nst > 0) insert(s0, j0);
+        if (nst > 1) insert(s1, j1);
+        if (nst > 2) insert(s2, j2);
+        if (nst > 3) insert(s3, j3);
+        if (tracing && lane == 0) {
+          p.trace[3 * nt + 0] = (unsigned long long)tr0;
+          p.trace[3 * nt + 1] = (unsigned long long)clock64();
+          p.trace[3 * nt + 2] = (unsigned long long)trc;
+        }
+      }
+      it += uint32_t(t1 - t0);
+      // ---- hand the list over
+      if (qb < p.nqb) {   // (the odd block out of a pair carries no queries)
+        uint64_t* dst = p.parts + (size_t(vslab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
+        for (int c = 0; c < p.kk; ++c) dst[c] = lds_u64(mylist + c * LSTRIDE);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still touch its barriers / tensor memory
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(sym);
+    return EncodeTiledFn(nullptr);
+  }();
+  return fn;
+}
+
+// Tensor maps depend only on (pointer, rows, dim): the last few are kept so that a steady stream of calls against
+// the same index (latency mode, every benchmark step) does not re-encode them.
+struct MapKey {
+  const void* ptr;
+  int64_t rows;
+  int dim;
+};
+static bool cached_map(const void* ptr, int64_t rows, int dim, CUtensorMap& out) {
+  constexpr int SLOTS = 8;
+  static std::mutex mu;
+  static MapKey keys[SLOTS];
+  static CUtensorMap maps[SLOTS];
+  static int next = 0, used = 0;
+  std::lock_guard<std::mutex> lk(mu);
+  for (int i = 0; i < used; ++i)
+    if (keys[i].ptr == ptr && keys[i].rows == rows && keys[i].dim == dim) {
+      out = maps[i];
+      return true;
+    }
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {cuuint64_t(dim), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(dim) * 2};
+  const cuuint32_t box[2] = {STAGE_K, HALF_N};
+  const cuuint32_t estride[2] = {1, 1};
+  CUtensorMap m;
+  if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  const int slot = used < SLOTS ? used++ : (next++ % SLOTS);
+  keys[slot] = MapKey{ptr, rows, dim};
+  maps[slot] = m;
+  out = m;
+  return true;
+}
+
+struct Plan {
+  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups;
+  size_t smem;
+};
+
+static size_t smem_bytes(int n_groups, int kk, int n_stages) {
+  return 1024 /*align*/ + size_t(n_stages) * STAGE_BYTES + size_t(n_groups) * kk * BLOCK_M * 8 +
+         size_t(4 * n_groups) * TILE_N * 4 + (2 * size_t(MAX_STAGES) + 4) * 8 + 64;
+}
+
+static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
+  if (dim <= 0 || dim % STAGE_K != 0 || dim > DRS_MAX_DIM) return false;
+  if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
+  const int g = sm_count();
+  if (g < 2) return false;
+  // two heaps per query (two epilogue groups) when four ring stages still fit; else one group and >= 2 stages
+  static const int want_groups = [] { const char* e = getenv("DRS_PAIR_GROUPS"); return e ? atoi(e) : 0; }();   // tuning hook
+  pl.n_groups = 2;
+  if (want_groups == 1 || smem_bytes(2, kk, 4) > SMEM_LIMIT) pl.n_groups = 1;
+  if (smem_bytes(pl.n_groups, kk, 2) > SMEM_LIMIT) return false;
+  int ns = 2;
+  while (ns < MAX_STAGES && smem_bytes(pl.n_groups, kk, ns + 1) <= SMEM_LIMIT) ++ns;
+  static const int cap_stages = [] { const char* e = getenv("DRS_PAIR_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
+  if (cap_stages >= 2 && ns > cap_stages) ns = cap_stages;
+  pl.n_stages = ns;
+  pl.smem = smem_bytes(pl.n_groups, kk, ns);
+  pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
+  pl.nqb2 = (pl.nqb + 1) / 2;
+  pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
+  // One item per CTA pair whenever the query blocks fit: every slab of a query block is then resident at the same
+  // time, which the pooled threshold relies on.
+  const int gp = g / 2;
+  int s = pl.nqb2 <= gp ? gp / pl.nqb2 : 1;
+  if (s > pl.n_tiles) s = pl.n_tiles;
+  pl.n_slabs = s < 1 ? 1 : s;
+  const int items = pl.nqb2 * pl.n_slabs;
+  pl.grid = 2 * (items < gp ? items : gp);
+  const int nv = pl.n_groups * pl.n_slabs;
+  const int m = (kk + nv - 1) / nv;
+  pl.m_rank = (items <= gp && m <= 6) ? m : 0;
+  return true;
+}
+
+}  // namespace ss2
+}  // namespace umma
+
+bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk) {
+  umma::ss2::Plan pl;
+  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) && umma::ss2::encode_tiled() != nullptr;
+}
+
+int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk) {
+  umma::ss2::Plan pl;
+  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs : 0;
+}
+
+// rows of the bf16 query image the kernel reads through TMA (workspace: rows * dim * 2 bytes, 128-byte aligned)
+int dense_pair_query_rows(int n_queries) { return ((n_queries + 255) / 256) * 256; }
+
+int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, int q_stride,
+                      uint32_t* d_gtau, void* d_qbf16, cudaStream_t st) {
+  using namespace umma;
+  using namespace umma::ss2;
+  Plan pl;
+  DRS_REQUIRE(make_plan(n_queries, n_rows, dim, kk, pl), DRS_ERR_UNSUPPORTED,
+              "dense(tcgen05 pair): needs dim % 64 == 0 and k' small enough for shared memory");
+  DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0, DRS_ERR_ARG, "dense: queries not 16-byte aligned");
+  DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_qbf16) & 127) == 0, DRS_ERR_ARG, "dense: query image not 128-byte aligned");
+  const int q_rows = dense_pair_query_rows(n_queries);
+  CUtensorMap tmap_q, tmap_c;
+  DRS_REQUIRE(cached_map(d_qbf16, q_rows, dim, tmap_q) && cached_map(d_corpus, n_rows, dim, tmap_c), DRS_ERR_CUDA,
+              "dense(tcgen05 pair): cuTensorMapEncodeTiled failed or is unavailable");
+  Params p;
+  p.inv_norm = d_inv_norm;
+  p.mask = d_mask;
+  p.parts = d_parts;
+  p.gtau = d_gtau;
+  p.gslab = d_gtau + q_stride;
+  p.n_rows = n_rows;
+  p.n_queries = n_queries;
+  p.nqb = pl.nqb;
+  p.nqb2 = pl.nqb2;
+  p.dim = dim;
+  p.kk = kk;
+  p.q_stride = q_stride;
+  p.n_slabs = pl.n_slabs;
+  p.n_tiles = pl.n_tiles;
+  p.n_stages = pl.n_stages;
+  p.m_rank = pl.m_rank;
+  p.n_groups = pl.n_groups;
+  static const uint32_t dbg = [] { const char* e = getenv("DRS_PAIR_DEBUG"); return e ? uint32_t(atoi(e)) : 0u; }();
+  p.debug = dbg;
+  // DRS_PAIR_TRACE=1 (debugging aid, synchronises): per-tile timeline of one epilogue warp on stderr
+  static const bool want_trace = getenv("DRS_PAIR_TRACE") != nullptr;
+  static unsigned long long* d_trace = nullptr;
+  if (want_trace && !d_trace) cudaMalloc(&d_trace, 3000 * sizeof(unsigned long long));
+  p.trace = want_trace ? d_trace : nullptr;
+  if (want_trace) cudaMemsetAsync(d_trace, 0, 3000 * sizeof(unsigned long long), st);
+  static std::once_flag attr_once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
+  });
+  DRS_CUDA_CHECK(attr_rc);
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
+  {
+    const int64_t n8 = int64_t(q_rows) * dim / 8;
+    const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 4 * sm_count()));
+    queries_to_bf16_kernel<<<blocks, 256, 0, st>>>(d_q, n_queries, q_rows, dim, reinterpret_cast<__nv_bfloat16*>(d_qbf16));
+    count_launches(1);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel, tmap_q, tmap_c, p));
+  count_launches(1);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  if (want_trace) {
+    static unsigned long long h[3000];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[pair trace] tiles/slab %d groups %d stages %d m_rank %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
+            pl.n_tiles / pl.n_slabs, pl.n_groups, pl.n_stages, pl.m_rank);
+    for (int i = 0; i < 1000 && h[3 * i + 1]; ++i)
+      fprintf(stderr, "[pair trace] %d %llu %llu %llu\n", i, h[3 * i] - h[0], h[3 * i + 1] - h[3 * i], h[3 * i + 2]);
+  }
+  return DRS_OK;
+}
+
+}  // namespace drs

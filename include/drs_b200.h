@@ -42,7 +42,11 @@ extern "C" {
 /* kernel family selector for drs_dense_topk */
 #define DRS_DENSE_AUTO 0
 #define DRS_DENSE_SIMT 1 /* fp32 CUDA-core streaming kernel (HBM-bound; small Q, any D%8==0) */
-#define DRS_DENSE_UMMA 2 /* tcgen05 bf16 GEMM + fused top-k epilogue (D%64==0, D<=768)    */
+#define DRS_DENSE_UMMA 2 /* tcgen05 bf16 GEMM + fused top-k epilogue; picks one of the two below  */
+#define DRS_DENSE_UMMA_TS 3   /* single-CTA form, queries parked in tensor memory (D%128==0, D<=768);
+                                 serves a single block of <= 128 queries                              */
+#define DRS_DENSE_UMMA_PAIR 4 /* CTA-pair form (cta_group::2, M256 x N256, both operands streamed by
+                                 TMA; D%64==0): the main kernel for >= 2 blocks of 128 queries        */
 
 int drs_version(void);
 const char* drs_last_error(void);
@@ -199,7 +203,8 @@ int drs_merge_candidates_f32(const float* d_scores, const int64_t* d_ids, int n_
 int drs_merge_candidates_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries,
                              int k, int k_out, double* d_out_scores, int64_t* d_out_ids, void* stream);
 
-/* Which kernel family the last drs_dense_topk call on this thread used (DRS_DENSE_SIMT/UMMA). */
+/* Which kernel the last drs_dense_topk call on this thread used: DRS_DENSE_SIMT (1), DRS_DENSE_UMMA (2, the
+ * single-CTA tensor kernel) or 3 (the CTA-pair tensor kernel). */
 int drs_dense_last_kernel(void);
 
 /* ---------------------------------------------------------------------------------

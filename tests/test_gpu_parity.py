@@ -98,11 +98,55 @@ def _umma_available():
 @pytest.mark.parametrize("n,q,kprime", [(64, 1, 4), (1000, 16, 10), (4099, 130, 10), (50000, 300, 10),
                                         (50000, 128, 60), (200000, 1000, 10), (30000, 257, 100)])
 def test_dense_umma_matches_oracle(n, q, kprime):
+    """The single-CTA tensor kernel (queries parked in tensor memory), forced."""
     if not _umma_available():
         pytest.skip("tcgen05 kernel not built")
     emb, qv = _dense_case(n, q, seed=n % 97 + q, dup_frac=0.001)
-    ties, flags = _check_dense(emb, qv, kprime, _lib.DENSE_UMMA)
+    ties, flags = _check_dense(emb, qv, kprime, _lib.DENSE_UMMA_TS)
     assert set(np.unique(flags).tolist()) <= {0, 2, 3}
+    assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
+
+
+# (rows, queries, k', dim): one tile, ragged tiles, odd number of query blocks (an idle half pair), one block
+# (half of every MMA is padding), k' classes with two / one epilogue groups, dims the single-CTA kernel cannot do
+@pytest.mark.parametrize("n,q,kprime,dim", [(64, 1, 4, 768), (255, 129, 10, 768), (4099, 130, 10, 768),
+                                            (50000, 300, 10, 768), (50000, 256, 60, 768), (200000, 1000, 10, 768),
+                                            (30000, 257, 100, 768), (70000, 700, 20, 768), (20000, 200, 10, 64),
+                                            (20000, 513, 10, 1024), (30000, 384, 30, 320)])
+def test_dense_pair_matches_oracle(n, q, kprime, dim):
+    """The CTA-pair tensor kernel (cta_group::2, M256 x N256, both operands streamed), forced."""
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(n, q, dim=dim, seed=n % 97 + q, dup_frac=0.001)
+    ties, flags = _check_dense(emb, qv, kprime, _lib.DENSE_UMMA_PAIR)
+    assert set(np.unique(flags).tolist()) <= {0, 2, 3}
+    assert _lib.load().drs_dense_last_kernel() == 3
+
+
+def test_dense_pair_mask_zero_rows_and_queries():
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(40000, 300, seed=21)
+    emb[17] = 0
+    emb[39999] = 0
+    qv[3] = 0
+    qv[299] = 0
+    mask = (np.random.default_rng(5).random(40000) < 0.4).astype(np.uint8)
+    _check_dense(emb, qv, 20, _lib.DENSE_UMMA_PAIR, mask=mask)
+    _check_dense(emb, qv, 20, _lib.DENSE_UMMA_PAIR)
+    mask[:] = 0
+    mask[[5, 99, 4000]] = 1      # fewer rows pass the filter than k'
+    _check_dense(emb, qv, 20, _lib.DENSE_UMMA_PAIR, mask=mask)
+
+
+def test_dense_tensor_dispatch():
+    """AUTO / UMMA: the pair kernel from two query blocks on, the single-CTA kernel for one block."""
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(20000, 300, seed=17)
+    _check_dense(emb, qv, 10, _lib.DENSE_AUTO)
+    assert _lib.load().drs_dense_last_kernel() == 3
+    _check_dense(emb, qv[:100].contiguous(), 10, _lib.DENSE_UMMA)
     assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
 
 
@@ -110,9 +154,10 @@ def test_dense_umma_without_escalation_flags_are_conservative():
     if not _umma_available():
         pytest.skip("tcgen05 kernel not built")
     emb, qv = _dense_case(100000, 256, seed=5)
-    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA, escalate=False)
-    assert set(np.unique(flags).tolist()) <= {0, 1}
-    assert (flags == 0).mean() > 0.5   # the bound proves most queries outright
+    for kernel in (_lib.DENSE_UMMA_TS, _lib.DENSE_UMMA_PAIR):
+        ties, flags = _check_dense(emb, qv, 10, kernel, escalate=False)
+        assert set(np.unique(flags).tolist()) <= {0, 1}
+        assert (flags == 0).mean() > 0.5   # the bound proves most queries outright
 
 
 def test_dense_umma_unnormalised_queries_and_proof_rate():
@@ -123,8 +168,9 @@ def test_dense_umma_unnormalised_queries_and_proof_rate():
     emb, qv = _dense_case(60000, 200, seed=13)
     qv[5] *= 37.5
     qv[6] *= 1e-3
-    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA, escalate=False)
-    assert (flags == 0).mean() > 0.97
+    for kernel in (_lib.DENSE_UMMA_TS, _lib.DENSE_UMMA_PAIR):
+        ties, flags = _check_dense(emb, qv, 10, kernel, escalate=False)
+        assert (flags == 0).mean() > 0.97
 
 
 def test_dense_umma_mask_and_auto_dispatch():
