@@ -99,7 +99,7 @@ static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim,
 
 struct DenseWs {
   size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, qimg_off, total;
-  int simt_parts, umma_parts, umma_qstride, variant;
+  int simt_parts, umma_parts, umma_qstride, variant, pool_parts;
 };
 
 static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
@@ -120,7 +120,11 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   w.flags_off = (w.parts_keys + w.cand_keys + w.scratch_keys) * 8;
   w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
   // bf16 image of the queries (the pair kernel's TMA source), 128-byte aligned
-  w.qimg_off = ((w.gtau_off + size_t(w.umma_qstride) * 4 * (1 + size_t(w.umma_parts)) + 255) / 256) * 256;
+  w.pool_parts = w.variant == TENSOR_PAIR ? dense_pair_pool_parts(n_queries, n_rows, dim, int(kk)) : w.umma_parts;
+  const size_t thr_words = w.variant == TENSOR_PAIR
+                               ? dense_pair_threshold_words(n_queries, n_rows, dim, int(kk), w.umma_qstride)
+                               : size_t(w.umma_qstride) * (1 + size_t(w.umma_parts));
+  w.qimg_off = ((w.gtau_off + thr_words * 4 + 255) / 256) * 256;
   w.total = w.qimg_off + (w.variant == TENSOR_PAIR ? size_t(dense_pair_query_rows(n_queries)) * dim * 2 : 0) + 256;
   return w;
 }
@@ -218,7 +222,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
     // the kernel's own thresholds (gtau, and the per-slab pooled bounds when pooling was on) pre-filter the merge
     const uint32_t* gtau = reinterpret_cast<const uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off);
     rc = launch_merge_keys_filtered(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, scratch, gtau,
-                                    gtau + w.umma_qstride, w.umma_parts, w.umma_qstride, st);
+                                    gtau + w.umma_qstride, w.pool_parts, w.umma_qstride, st);
   }
   if (rc != DRS_OK) return rc;
   rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,

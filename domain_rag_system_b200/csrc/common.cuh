@@ -172,6 +172,8 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
 bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk);
 int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk);
 int dense_pair_query_rows(int n_queries);
+int dense_pair_pool_parts(int n_queries, int64_t n_rows, int dim, int kk);
+size_t dense_pair_threshold_words(int n_queries, int64_t n_rows, int dim, int kk, int q_stride);
 int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                       const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
                       int q_stride, uint32_t* d_gtau, void* d_qbf16, cudaStream_t st);

@@ -40,7 +40,6 @@ constexpr int STAGE_K = 64;                          // K elements per ring stag
 constexpr int A_BYTES = BLOCK_M * STAGE_K * 2;       // 16384: my 128 queries x 64
 constexpr int B_BYTES = HALF_N * STAGE_K * 2;        // 16384: my 128 corpus rows x 64
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // 32768 per CTA
-constexpr int THREADS = 384;
 constexpr int MAX_STAGES = 6;
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 // D = f32, A = B = bf16, both K-major, N = 256, M = 256 (over the pair)
@@ -52,12 +51,14 @@ struct Params {
   const uint8_t* mask;
   uint64_t* parts;
   uint32_t* gtau;    // [q_stride] zero-initialised shared thresholds
-  uint32_t* gslab;   // [n_vslabs][q_stride] zero-initialised: each virtual slab's m_rank-th best inserted score
+  uint32_t* gslab;   // [n_vslabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
+  uint32_t* seed_cnt;// [2 * nqb2] zero-initialised: epilogue warps of a query block that are past their seed pass
   int64_t n_rows;
   int n_queries, nqb, nqb2, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
-  int m_rank;        // ceil(kk / n_vslabs) if <= 6 and every slab of a query block is resident at once, else 0
+  int pool_g;        // pool parts per virtual slab (1, 2, 4, 8: column groups of a tile), 0 = pooling off
   int n_groups;      // epilogue warp groups == candidate heaps per query per CTA
-  uint32_t debug;    // timing experiments only (results are garbage): 1 no inserts, 2 no epilogue work
+  uint32_t debug;    // timing experiments only (results are garbage): 1 no inserts, 2 no epilogue work,
+                     // 4 no threshold publishing, 8 no list work
   unsigned long long* trace;   // DRS_PAIR_TRACE: per tile of block 0 / warp 4: {clock at accumulator ready, clock at
                                // tile done, flagged columns}; NULL otherwise
 };
@@ -95,48 +96,12 @@ __global__ void __launch_bounds__(256) queries_to_bf16_kernel(const float* __res
   }
 }
 
-// Per-lane (= per query) candidate list state.  It lives in local memory (its address is taken by the out-of-line
-// insert below) and is touched only on the rare survivor path; the hot loop carries `tau` in a register.
-struct LaneState {
-  uint64_t root;     // the heap's root = kk-th best candidate once the list is full, 0 before
-  int cnt;           // entries while the list fills by plain appends; == kk once it is a heap
-  float tau_loc;     // score of the root
-  float tm[6];       // this virtual slab's six best inserted scores, descending
-};
-
-// One survivor into a lane's list.  Out of line on purpose: inlined at every call site the heap code made the
-// epilogue loop larger than the instruction cache.  Returns the lane's new local threshold.
-__device__ __noinline__ float lane_insert(LaneState& st, uint32_t mylist, int kk, int m_rank, float s, uint32_t row,
-                                          volatile uint32_t* gs, uint32_t* gt) {
-  const uint64_t key = make_key(s, row);
-  const bool filling = st.cnt < kk;
-  if (!filling && key <= st.root) return st.tau_loc;
-  if (filling) {
-    sts_u64(mylist + st.cnt * LSTRIDE, key);
-    if (++st.cnt == kk) st.root = heap_build(mylist, kk);
-  } else {
-    st.root = heap_replace_root(mylist, kk, key);
-  }
-  if (m_rank > 0 && s > st.tm[5]) {   // keep the six best scores, publish the m-th
-    float a0 = st.tm[0], a1 = st.tm[1], a2 = st.tm[2], a3 = st.tm[3], a4 = st.tm[4], a5 = s;
-    if (a5 > a4) { const float x = a4; a4 = a5; a5 = x; }
-    if (a4 > a3) { const float x = a3; a3 = a4; a4 = x; }
-    if (a3 > a2) { const float x = a2; a2 = a3; a3 = x; }
-    if (a2 > a1) { const float x = a1; a1 = a2; a2 = x; }
-    if (a1 > a0) { const float x = a0; a0 = a1; a1 = x; }
-    st.tm[0] = a0; st.tm[1] = a1; st.tm[2] = a2; st.tm[3] = a3; st.tm[4] = a4; st.tm[5] = a5;
-    const float mth = m_rank == 1 ? a0 : (m_rank == 2 ? a1 : (m_rank == 3 ? a2 : (m_rank == 4 ? a3 : (m_rank == 5 ? a4 : a5))));
-    if (mth > -INFINITY) *gs = ord32(mth);
-  }
-  if (st.root) {
-    st.tau_loc = key_score(st.root);
-    atomicMax(gt, ord32(st.tau_loc));
-  }
-  return st.tau_loc;
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
+// NG = epilogue warp groups (p.n_groups): two (384 threads, 168 registers each) for short lists, one (256 threads,
+// 255 registers) otherwise; GMAX = pool parts per virtual slab this instantiation can track in registers.
+template <int NG>
+__global__ void __launch_bounds__(128 + 128 * NG, 1)
 dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, Params p) {
+  constexpr int GMAX = NG == 2 ? 2 : 8;
   const uint32_t rank = cluster_ctarank();            // 0 = leader
   const int cta = int(blockIdx.x >> 1);               // work-item stream this pair walks
   const int n_ctas = int(gridDim.x >> 1);
@@ -256,7 +221,7 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
     }
-  } else if (warp >= 4 && warp < 4 + 4 * p.n_groups) {
+  } else if (warp >= 4) {
     // ===================================================================== epilogue
     // Group g owns accumulator stage g and every other tile (two tile-times to drain one tile); a single group
     // owns both stages.  Each group keeps its own heap per query: a "virtual slab" of the corpus.
@@ -264,11 +229,14 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int grp = (warp - 4) >> 2;
     const int L = ew * 32 + lane;            // TMEM lane == query within my block
     const uint32_t lane_addr = uint32_t(ew * 32) << 16;
-    const int ng = p.n_groups;
+    constexpr int ng = NG;
     const uint32_t mylist = smem_u32(lists) + uint32_t(grp * p.kk * BLOCK_M + L) * 8;   // my heap's slot 0
-    float* nstrip = norm_strips + (warp - 4) * TILE_N;
+    const uint32_t nstrip = smem_u32(norm_strips + (warp - 4) * TILE_N);                // this warp's norm strip
     const uint32_t tempty_leader = mapa_u32(smem_u32(tempty), 0);
     const bool no_insert = (p.debug & 1) != 0;
+    const int G = p.pool_g;
+    const int n_vslabs = ng * p.n_slabs;
+    const int n_pool = n_vslabs * G;
     uint32_t it = 0;                         // tiles issued so far, mirrors the MMA warp
     for (int item = cta; item < n_items; item += n_ctas) {
       const int qb = 2 * (item % p.nqb2) + int(rank), slab = item / p.nqb2;
@@ -279,26 +247,36 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
       // The list fills by plain appends (cnt < kk), is turned into a min-heap once (Floyd), and from then on its
       // root is the kk-th best candidate: replacing it costs O(log kk).
-      LaneState st;
-      st.root = 0;
-      st.cnt = 0;
-      st.tau_loc = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) st.tm[i] = -INFINITY;
+      int cnt = 0;
+      uint64_t root = 0;
       // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by every heap working
-      // on q (ordered-u32 image, atomicMax): slabs warm each other's thresholds.  Padding lanes never insert.
+      // on q (ordered-u32 image, atomicMax).  Padding lanes never insert.
       uint32_t* gt = p.gtau + (live ? q : 0);
       uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
-      // Pooled threshold: all virtual slabs of a query block run concurrently, each publishes the m-th best score
-      // it has inserted so far in gslab[vslab][q] (m = ceil(kk / #virtual slabs) <= 6).  If every one of them has m
-      // rows scoring >= x, the corpus has >= kk such rows: x = min over virtual slabs is a valid lower bound of the
-      // global kk-th best, and far tighter than any local bound while the lists warm up.
+      // Pooled threshold.  The corpus is cut into n_pool = (#virtual slabs x G) disjoint PARTS: part (v, g) = the rows
+      // of virtual slab v that sit in column group g of their tile.  All virtual slabs of a query block run
+      // concurrently and publish the running MAXIMUM of each of their parts in gslab[part][q].  If every part has a
+      // row scoring >= x the corpus has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound
+      // of the global kk-th best -- and far tighter than any local bound while the lists warm up.
       const int vslab = slab * ng + grp;
-      volatile uint32_t* gs = p.gslab + size_t(vslab) * p.q_stride + (live ? q : 0);
+      volatile uint32_t* gs = p.gslab + size_t(vslab) * G * p.q_stride + (live ? q : 0);
+      float pm[GMAX];
+#pragma unroll
+      for (int i = 0; i < GMAX; ++i) pm[i] = -INFINITY;
+      auto pm_fold = [&](int g, float v) {   // pm[g] = max(pm[g], v) for a runtime g, registers only
+#pragma unroll
+        for (int i = 0; i < GMAX; ++i) pm[i] = (g == i) ? fmaxf(pm[i], v) : pm[i];
+      };
       float tau_pool = -INFINITY;
       float tau_loc = -INFINITY;
-      const int n_vslabs = ng * p.n_slabs;
-      const int pool_every = n_vslabs > 32 ? n_vslabs / 4 : 8;
+      auto refresh_pool = [&]() {
+        if (live) {
+          uint32_t mn = 0xffffffffu;
+          const volatile uint32_t* col = p.gslab + q;
+          for (int sl = 0; sl < n_pool; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
+          if (mn != 0u) tau_pool = fmaxf(tau_pool, unord32(mn));   // 0 = some part has not reported yet
+        }
+      };
       // inverse norms of the tile's 256 rows: lane l fetches rows 8l..8l+7 one tile ahead, parks them in this warp's
       // strip, and every lane reads all of them by broadcast
       float4 nA, nB;
@@ -316,35 +294,83 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       };
       const int t_first = (ng == 1) ? t0 : t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of the item
+      // Seed rendezvous (pooling only): every epilogue warp working on this block of 128 queries counts itself in
+      // once its first tile's part maxima are published (or at once if it has no tile / cannot seed).
+      const uint32_t seed_expect = uint32_t(p.n_slabs * ng * 4);
+      uint32_t* seed_ctr = p.seed_cnt + qb;
+      const bool seeding = G > 0 && p.mask == nullptr && !(p.debug & 16);
+      if (seeding && t_first >= t1 && lane == 0) atomicAdd(seed_ctr, 1u);
       load_norms(t_first);
-      int nt = 0;
+      int nt = 0, next_refresh = 1;
       for (int t = t_first; t < t1; t += ng, ++nt) {
         const uint32_t itt = it + uint32_t(t - t0);      // this tile's global sequence number
         __syncwarp();                                    // everyone is done reading the previous tile's strip
-        reinterpret_cast<float4*>(nstrip)[2 * lane] = nA;
-        reinterpret_cast<float4*>(nstrip)[2 * lane + 1] = nB;
+        sts_f32x4(nstrip + 32 * lane, nA);
+        sts_f32x4(nstrip + 32 * lane + 16, nB);
         __syncwarp();
         load_norms(t + ng);                              // prefetch for my next tile
-        // refreshed before each of the first tiles (thresholds move fastest while the heaps fill), then periodically
-        if (live && p.m_rank > 0 && (nt < 8 || (nt % pool_every) == pool_every - 1)) {
-          uint32_t mn = 0xffffffffu;
-          const volatile uint32_t* col = p.gslab + q;
-          for (int sl = 0; sl < n_vslabs; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
-          if (mn != 0u) tau_pool = fmaxf(tau_pool, unord32(mn));   // 0 = some slab has not reported yet
+        // the pooled bound moves fastest early on: refreshed before tiles 1, 2, 3, 4, 6, 9, 13, ... then every 32nd
+        if (G > 0 && nt == next_refresh) {
+          refresh_pool();
+          next_refresh += min(32, max(1, nt >> 1));
         }
-        float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
-        if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);   // lands while this tile is processed
         const uint32_t as = itt & 1u, aph = (itt >> 1) & 1;
         mbar_wait(tfull + as, aph, 5);
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + lane_addr + as * TILE_N;
-        auto insert = [&](float s, int j) {
-          const int64_t row = int64_t(t) * TILE_N + j;
-          if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
-            tau_loc = lane_insert(st, mylist, p.kk, p.m_rank, s, uint32_t(row), gs, gt);
-            tau = fmaxf(tau, tau_loc);
+        if (seeding && nt == 0) {
+          // ---- seed pass over my FIRST tile: nothing is inserted; the maximum of each of its 8 sub-chunks of 32
+          // columns is folded into the G part maxima and published, then the warp waits (bounded) until every
+          // virtual slab of this query block has done the same.  The first real pass then starts from a threshold
+          // that only ~kk / (rows seen by all slabs) of the scores reach, instead of from -infinity.
+          if (int64_t(t + 1) * TILE_N <= p.n_rows) {   // (a ragged tile has padding rows: it cannot seed)
+#pragma unroll 1
+            for (int ch = 0; ch < TILE_N / 64; ++ch) {
+              uint32_t acc0[32], acc1[32];
+              tmem_ld32(taddr0 + ch * 64, acc0);
+              tmem_ld32(taddr0 + ch * 64 + 32, acc1);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+              float a = -INFINITY, b = -INFINITY;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 n = lds_f32x4(nstrip + (ch * 64 + 4 * g) * 4);
+                a = fmaxf(a, fmaxf(fmaxf(__uint_as_float(acc0[4 * g + 0]) * n.x, __uint_as_float(acc0[4 * g + 1]) * n.y),
+                                   fmaxf(__uint_as_float(acc0[4 * g + 2]) * n.z, __uint_as_float(acc0[4 * g + 3]) * n.w)));
+              }
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 n = lds_f32x4(nstrip + (ch * 64 + 32 + 4 * g) * 4);
+                b = fmaxf(b, fmaxf(fmaxf(__uint_as_float(acc1[4 * g + 0]) * n.x, __uint_as_float(acc1[4 * g + 1]) * n.y),
+                                   fmaxf(__uint_as_float(acc1[4 * g + 2]) * n.z, __uint_as_float(acc1[4 * g + 3]) * n.w)));
+              }
+              // column group of sub-chunk sc (32 columns): (sc * G) >> 3
+              pm_fold(((2 * ch) * G) >> 3, a);
+              pm_fold(((2 * ch + 1) * G) >> 3, b);
+            }
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < GMAX; ++i)
+                if (i < G) gs[size_t(i) * p.q_stride] = ord32(pm[i]);
+            }
           }
-        };
+          __threadfence();
+          __syncwarp();
+          int all_in = 0;
+          if (lane == 0) {
+            atomicAdd(seed_ctr, 1u);
+            const long long w0 = clock64();
+            do {
+              all_in = *reinterpret_cast<volatile uint32_t*>(seed_ctr) >= seed_expect ? 1 : 0;
+            } while (!all_in && clock64() - w0 < 60000);
+          }
+          all_in = __shfl_sync(0xffffffffu, all_in, 0);
+          if (all_in) {
+            __threadfence();
+            refresh_pool();
+          }
+        }
+        float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
+        if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);   // lands while this tile is processed
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nst = 0;
         const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && nt < 1000;
@@ -354,69 +380,108 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // Survivors of pass 1 are taken out of the REGISTERS the accumulator chunk was loaded into: every lane
         // that has flagged columns picks ITS OWN lowest one through a select tree, so a round serves up to 32
         // different columns at once and a chunk costs max-over-lanes(#flagged) rounds, not #distinct columns.
-        // The first four survivors of a tile are only stashed; their heap work runs after the accumulator has
-        // been handed back.
-        auto rounds = [&](uint32_t m, const uint32_t (&acc)[32], int col0) {
-          while (__any_sync(0xffffffffu, m != 0)) {
-            ++trc;
-            if (m != 0) {
-              const int j = __ffs(m) - 1;
-              m &= m - 1;
-              const int jj = col0 + j;
-              const float s = __uint_as_float(pick32(acc, j)) * nstrip[jj];
+        // A survivor is first parked in a four-entry register stash; the heap work happens in ONE place (the drain
+        // at the bottom of the loop: the list code is large, and inlined at several sites it overflowed the
+        // instruction cache), when some lane's stash is full or the tile is done.  Iteration TILE_N/64 of the
+        // chunk loop only drains.
+#pragma unroll 1
+        for (int ch = 0; ch <= TILE_N / 64; ++ch) {   // 64 accumulator columns at a time
+          uint32_t acc0[32], acc1[32];
+          uint32_t m0 = 0, m1 = 0;
+          const bool last = ch == TILE_N / 64;
+          if (!last) {
+            const uint32_t taddr = taddr0 + ch * 64;
+            if (!(p.debug & 2)) {
+              tmem_ld32(taddr, acc0);
+              tmem_ld32(taddr + 32, acc1);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            }
+            if (ch == TILE_N / 64 - 1) {   // the whole tile has been read: hand the accumulator back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + as * 8);
+            }
+            if (!(p.debug & 2)) {
+              // ---- pass 1, branch-free: which of these 64 scores reach the threshold?
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 n = lds_f32x4(nstrip + (ch * 64 + 4 * g) * 4);
+                m0 |= (__uint_as_float(acc0[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+                m0 |= (__uint_as_float(acc0[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+                m0 |= (__uint_as_float(acc0[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+                m0 |= (__uint_as_float(acc0[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+              }
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 n = lds_f32x4(nstrip + (ch * 64 + 32 + 4 * g) * 4);
+                m1 |= (__uint_as_float(acc1[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
+                m1 |= (__uint_as_float(acc1[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
+                m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
+                m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
+              }
+              if (no_insert) m0 = m1 = 0;
+            }
+          }
+          // ---- pass 2, rare and rolled
+          bool more;
+          do {
+            if ((m0 | m1) != 0 && nst < 4) {
+              const bool hi = m0 == 0;
+              const uint32_t mm = hi ? m1 : m0;
+              const int j = __ffs(mm) - 1;
+              if (hi) m1 = mm & (mm - 1);
+              else m0 = mm & (mm - 1);
+              const uint32_t v0 = pick32(acc0, j), v1 = pick32(acc1, j);
+              const int jj = ch * 64 + (hi ? 32 : 0) + j;
+              const float s = __uint_as_float(hi ? v1 : v0) * lds_f32(nstrip + jj * 4);
               if (nst == 0) { s0 = s; j0 = jj; }
               else if (nst == 1) { s1 = s; j1 = jj; }
               else if (nst == 2) { s2 = s; j2 = jj; }
-              else if (nst == 3) { s3 = s; j3 = jj; }
-              else insert(s, jj);                // stash full (warm-up tiles only): insert in place
+              else { s3 = s; j3 = jj; }
               ++nst;
             }
-          }
-        };
-#pragma unroll 1
-        for (int ch = 0; ch < TILE_N / 64; ++ch) {   // 64 accumulator columns at a time
-          uint32_t acc0[32], acc1[32];
-          const uint32_t taddr = taddr0 + ch * 64;
-          if (!(p.debug & 2)) {
-            tmem_ld32(taddr, acc0);
-            tmem_ld32(taddr + 32, acc1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          }
-          if (ch == TILE_N / 64 - 1) {   // the whole tile is in registers (or done): hand the accumulator back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(tempty_leader + as * 8);
-          }
-          if (p.debug & 2) continue;
-          // ---- pass 1, branch-free: which of these 64 scores reach the threshold?
-          uint32_t m0 = 0, m1 = 0;
-          const float4* nb4 = reinterpret_cast<const float4*>(nstrip + ch * 64);
+            more = __any_sync(0xffffffffu, (m0 | m1) != 0);
+            const bool drain = more ? __any_sync(0xffffffffu, nst == 4) : (last && __any_sync(0xffffffffu, nst > 0));
+            if (drain) {
+              ++trc;
+              for (int i = 0; i < nst; ++i) {
+                const float s = i == 0 ? s0 : (i == 1 ? s1 : (i == 2 ? s2 : s3));
+                const int j = i == 0 ? j0 : (i == 1 ? j1 : (i == 2 ? j2 : j3));
+                const int64_t row = int64_t(t) * TILE_N + j;
+                if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
+                  const uint64_t key = make_key(s, uint32_t(row));
+                  const bool filling = cnt < p.kk;
+                  if (filling || key > root) {
+                    if (p.debug & 8) {   // timing experiment: no list work at all
+                      root = key;
+                    } else if (filling) {
+                      sts_u64(mylist + cnt * LSTRIDE, key);
+                      if (++cnt == p.kk) root = heap_build(mylist, p.kk);
+                    } else {
+                      root = heap_replace_root(mylist, p.kk, key);
+                    }
+                    if (G > 0) {   // running maximum of the row's pool part
+                      const int g = ((j >> 5) * G) >> 3;
+                      float cur = pm[0];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 n = nb4[g];
-            m0 |= (__uint_as_float(acc0[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
-            m0 |= (__uint_as_float(acc0[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
-            m0 |= (__uint_as_float(acc0[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
-            m0 |= (__uint_as_float(acc0[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
-          }
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float4 n = nb4[8 + g];
-            m1 |= (__uint_as_float(acc1[4 * g + 0]) * n.x >= tau) ? (1u << (4 * g + 0)) : 0u;
-            m1 |= (__uint_as_float(acc1[4 * g + 1]) * n.y >= tau) ? (1u << (4 * g + 1)) : 0u;
-            m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
-            m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
-          }
-          if (no_insert) m0 = m1 = 0;
-          // ---- pass 2, rare and rolled
-          rounds(m0, acc0, ch * 64);
-          rounds(m1, acc1, ch * 64 + 32);
+                      for (int i = 1; i < GMAX; ++i) cur = (g == i) ? pm[i] : cur;
+                      if (s > cur) {
+                        pm_fold(g, s);
+                        if (!(p.debug & 4)) gs[size_t(g) * p.q_stride] = ord32(s);
+                      }
+                    }
+                    if (root) {
+                      tau_loc = key_score(root);
+                      tau = fmaxf(tau, tau_loc);
+                      if (!(p.debug & 4)) atomicMax(gt, ord32(tau_loc));
+                    }
+                  }
+                }
+              }
+              nst = 0;
+            }
+          } while (more);
         }
-        // ---- the stashed survivors
-        if (nst > 0) insert(s0, j0);
-        if (nst > 1) insert(s1, j1);
-        if (nst > 2) insert(s2, j2);
-        if (nst > 3) insert(s3, j3);
         if (tracing && lane == 0) {
           p.trace[3 * nt + 0] = (unsigned long long)tr0;
           p.trace[3 * nt + 1] = (unsigned long long)clock64();
@@ -495,7 +560,7 @@ static bool cached_map(const void* ptr, int64_t rows, int dim, CUtensorMap& out)
 }
 
 struct Plan {
-  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, m_rank, n_groups;
+  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, pool_g, n_groups;
   size_t smem;
 };
 
@@ -531,9 +596,16 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   pl.n_slabs = s < 1 ? 1 : s;
   const int items = pl.nqb2 * pl.n_slabs;
   pl.grid = 2 * (items < gp ? items : gp);
+  // pool parts: the smallest G in {1, 2, 4, 8} with (#virtual slabs x G) >= kk; pooling needs every virtual slab of
+  // a query block resident at the same time (one item per pair)
   const int nv = pl.n_groups * pl.n_slabs;
-  const int m = (kk + nv - 1) / nv;
-  pl.m_rank = (items <= gp && m <= 6) ? m : 0;
+  pl.pool_g = 0;
+  if (items <= gp)
+    for (int g = 1; g <= (pl.n_groups == 2 ? 2 : 8); g <<= 1)
+      if (nv * g >= kk) {
+        pl.pool_g = g;
+        break;
+      }
   return true;
 }
 
@@ -548,6 +620,18 @@ bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk) {
 int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk) {
   umma::ss2::Plan pl;
   return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs : 0;
+}
+
+// pool parts (rows of the per-part threshold table right after gtau[q_stride]) and the u32 words of the whole
+// zero-initialised threshold area: gtau[q_stride] | gslab[pool parts][q_stride] | seed counters
+int dense_pair_pool_parts(int n_queries, int64_t n_rows, int dim, int kk) {
+  umma::ss2::Plan pl;
+  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs * pl.pool_g : 0;
+}
+size_t dense_pair_threshold_words(int n_queries, int64_t n_rows, int dim, int kk, int q_stride) {
+  umma::ss2::Plan pl;
+  if (!umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl)) return 0;
+  return size_t(q_stride) * (1 + size_t(pl.n_groups) * pl.n_slabs * pl.pool_g) + 2 * size_t(pl.nqb2) + 8;
 }
 
 // rows of the bf16 query image the kernel reads through TMA (workspace: rows * dim * 2 bytes, 128-byte aligned)
@@ -573,6 +657,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   p.parts = d_parts;
   p.gtau = d_gtau;
   p.gslab = d_gtau + q_stride;
+  p.seed_cnt = d_gtau + size_t(q_stride) * (1 + size_t(pl.n_groups) * pl.n_slabs * pl.pool_g);
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -583,7 +668,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_slabs = pl.n_slabs;
   p.n_tiles = pl.n_tiles;
   p.n_stages = pl.n_stages;
-  p.m_rank = pl.m_rank;
+  p.pool_g = pl.pool_g;
   p.n_groups = pl.n_groups;
   static const uint32_t dbg = [] { const char* e = getenv("DRS_PAIR_DEBUG"); return e ? uint32_t(atoi(e)) : 0u; }();
   p.debug = dbg;
@@ -596,10 +681,12 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   static std::once_flag attr_once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
+    attr_rc = cudaFuncSetAttribute(dense_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
+    if (attr_rc == cudaSuccess)
+      attr_rc = cudaFuncSetAttribute(dense_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
   });
   DRS_CUDA_CHECK(attr_rc);
-  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, dense_pair_threshold_words(n_queries, n_rows, dim, kk, q_stride) * sizeof(uint32_t), st));
   {
     const int64_t n8 = int64_t(q_rows) * dim / 8;
     const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 4 * sm_count()));
@@ -608,7 +695,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(128 + 128 * pl.n_groups);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -618,15 +705,16 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel, tmap_q, tmap_c, p));
+  if (pl.n_groups == 2) DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel<2>, tmap_q, tmap_c, p));
+  else DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel<1>, tmap_q, tmap_c, p));
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   if (want_trace) {
     static unsigned long long h[3000];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pair trace] tiles/slab %d groups %d stages %d m_rank %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
-            pl.n_tiles / pl.n_slabs, pl.n_groups, pl.n_stages, pl.m_rank);
+    fprintf(stderr, "[pair trace] tiles/slab %d groups %d stages %d pool_g %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
+            pl.n_tiles / pl.n_slabs, pl.n_groups, pl.n_stages, pl.pool_g);
     for (int i = 0; i < 1000 && h[3 * i + 1]; ++i)
       fprintf(stderr, "[pair trace] %d %llu %llu %llu\n", i, h[3 * i] - h[0], h[3 * i + 1] - h[3 * i], h[3 * i + 2]);
   }
