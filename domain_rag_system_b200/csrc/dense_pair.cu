@@ -12,12 +12,12 @@
 //   D          = 2 x (128 lanes x 256 columns) fp32 in tensor memory: ALL 512 columns, double buffered, so the
 //                epilogue of tile t overlaps the MMAs of tile t+1.
 //   epilogue   = lane L of a CTA is query L of its block; after tcgen05.ld a thread holds its query's 256 scores of the
-//                tile, scales them by inv_norm[row] and compares against its threshold; the rare survivors go to a
-//                thread-private min-heap in shared memory.  Never writes scores.
+//                tile, scales them by inv_norm[row] and compares against its threshold; the rare survivors go to the
+//                query's min-heap in shared memory.  Never writes scores.
 //
 // Roles per CTA (384 threads): warp 0 TMA producer (each CTA loads ITS halves), warp 1 MMA issuer (leader CTA only,
-// one elected lane), warp 2 tensor-memory allocator, warps 4..11 two epilogue groups (one group when the heaps of a
-// large k' leave no room for two).  Work item = (pair of query blocks, slab of corpus tiles); the pairs that run
+// one elected lane), warp 2 tensor-memory allocator, warps 4..11 two epilogue groups that alternate tiles and share
+// ONE candidate list per query (per-lane lock).  Work item = (pair of query blocks, slab of corpus tiles); the pairs that run
 // concurrently cover the same slab for different query blocks, so the corpus leaves HBM about once.
 // Output: one partial list of kk keys per (virtual slab, query); merged and exactly re-scored downstream (select.cu).
 #include <cuda.h>
@@ -51,12 +51,11 @@ struct Params {
   const uint8_t* mask;
   uint64_t* parts;
   uint32_t* gtau;    // [q_stride] zero-initialised shared thresholds
-  uint32_t* gslab;   // [n_vslabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
+  uint32_t* gslab;   // [n_slabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
   uint32_t* seed_cnt;// [2 * nqb2] zero-initialised: epilogue warps of a query block that are past their seed pass
   int64_t n_rows;
   int n_queries, nqb, nqb2, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
-  int pool_g;        // pool parts per virtual slab (1, 2, 4, 8: column groups of a tile), 0 = pooling off
-  int n_groups;      // epilogue warp groups == candidate heaps per query per CTA
+  int pool_g;        // pool parts per slab (1, 2, 4, 8: column groups of a tile), 0 = pooling off
   uint32_t debug;    // timing experiments only (results are garbage): 1 no inserts, 2 no epilogue work,
                      // 4 no threshold publishing, 8 no list work
   unsigned long long* trace;   // DRS_PAIR_TRACE: per tile of block 0 / warp 4: {clock at accumulator ready, clock at
@@ -96,21 +95,24 @@ __global__ void __launch_bounds__(256) queries_to_bf16_kernel(const float* __res
   }
 }
 
-// NG = epilogue warp groups (p.n_groups): two (384 threads, 168 registers each) for short lists, one (256 threads,
-// 255 registers) otherwise; GMAX = pool parts per virtual slab this instantiation can track in registers.
-template <int NG>
-__global__ void __launch_bounds__(128 + 128 * NG, 1)
+constexpr int THREADS = 384;                         // 4 service warps + 2 epilogue groups of 4 warps
+constexpr int POOL_GMAX = 8;                         // pool parts per slab at most (column groups of a tile)
+constexpr int EPI_BAR = 1;                           // named barrier of the 8 epilogue warps
+
+__global__ void __launch_bounds__(THREADS, 1)
 dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, Params p) {
-  constexpr int GMAX = NG == 2 ? 2 : 8;
   const uint32_t rank = cluster_ctarank();            // 0 = leader
   const int cta = int(blockIdx.x >> 1);               // work-item stream this pair walks
   const int n_ctas = int(gridDim.x >> 1);
   extern __shared__ uint8_t smem_dyn[];
-  // carve: [ring | heaps | norm strips | barriers | tmem slot]; the swizzled ring needs 1024-byte alignment
+  // carve: [ring | list | lane state | part maxima | norm strips | barriers | tmem slot]; the swizzled ring needs
+  // 1024-byte alignment
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);
-  float* norm_strips = reinterpret_cast<float*>(lists + size_t(p.n_groups) * p.kk * BLOCK_M);   // [warps][TILE_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_strips + size_t(4 * p.n_groups) * TILE_N);
+  uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);        // [kk][128] keys
+  uint8_t* lstate = reinterpret_cast<uint8_t*>(lists + size_t(p.kk) * BLOCK_M);                  // [128] {root, cnt, lock}
+  uint32_t* pmem = reinterpret_cast<uint32_t*>(lstate + BLOCK_M * 16);                            // [pool_g][128] ord32
+  float* norm_strips = reinterpret_cast<float*>(pmem + size_t(p.pool_g) * BLOCK_M);              // [8 warps][TILE_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_strips + 8 * TILE_N);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.n_stages;
   uint64_t* tfull = bars + 2 * p.n_stages;
@@ -223,20 +225,23 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue
-    // Group g owns accumulator stage g and every other tile (two tile-times to drain one tile); a single group
-    // owns both stages.  Each group keeps its own heap per query: a "virtual slab" of the corpus.
+    // Two groups of four warps; group g owns accumulator stage g and every other tile, i.e. has two tile-times to
+    // drain one tile.  Lane L of BOTH groups is query L of the block: the two threads share ONE candidate list
+    // (and its state: root, fill count, part maxima) in shared memory, guarded by a per-lane lock -- survivors are
+    // rare, so the lock is almost never contended, and the list memory of a second heap buys ring stages instead.
     const int ew = warp & 3;                 // the TMEM sub-partition (lanes 32*ew ..) this warp may touch
     const int grp = (warp - 4) >> 2;
     const int L = ew * 32 + lane;            // TMEM lane == query within my block
     const uint32_t lane_addr = uint32_t(ew * 32) << 16;
-    constexpr int ng = NG;
-    const uint32_t mylist = smem_u32(lists) + uint32_t(grp * p.kk * BLOCK_M + L) * 8;   // my heap's slot 0
-    const uint32_t nstrip = smem_u32(norm_strips + (warp - 4) * TILE_N);                // this warp's norm strip
+    const uint32_t mylist = smem_u32(lists) + uint32_t(L) * 8;          // slot 0 of lane L's list
+    const uint32_t st_root = smem_u32(lstate) + uint32_t(L) * 16;       // u64 root (0 until the list is a heap)
+    const uint32_t st_cnt = st_root + 8, st_lock = st_root + 12;        // u32 entries while filling, u32 lock
+    const uint32_t pm_addr = smem_u32(pmem) + uint32_t(L) * 4;          // part g at + g * 512
+    const uint32_t nstrip = smem_u32(norm_strips + (warp - 4) * TILE_N);   // this warp's norm strip
     const uint32_t tempty_leader = mapa_u32(smem_u32(tempty), 0);
     const bool no_insert = (p.debug & 1) != 0;
     const int G = p.pool_g;
-    const int n_vslabs = ng * p.n_slabs;
-    const int n_pool = n_vslabs * G;
+    const int n_pool = p.n_slabs * G;
     uint32_t it = 0;                         // tiles issued so far, mirrors the MMA warp
     for (int item = cta; item < n_items; item += n_ctas) {
       const int qb = 2 * (item % p.nqb2) + int(rank), slab = item / p.nqb2;
@@ -244,31 +249,26 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       slab_tiles(slab, t0, t1);
       const int q = qb * BLOCK_M + L;
       const bool live = q < p.n_queries;
-      for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
       // The list fills by plain appends (cnt < kk), is turned into a min-heap once (Floyd), and from then on its
       // root is the kk-th best candidate: replacing it costs O(log kk).
-      int cnt = 0;
-      uint64_t root = 0;
-      // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by every heap working
+      if (grp == 0) {
+        for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
+        sts_u64(st_root, 0);
+        sts_u64(st_cnt, 0);   // cnt and lock
+        for (int g = 0; g < G; ++g) sts_u32(pm_addr + g * 512, 0u);
+      }
+      named_bar_sync(EPI_BAR, 256);
+      // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by every list working
       // on q (ordered-u32 image, atomicMax).  Padding lanes never insert.
       uint32_t* gt = p.gtau + (live ? q : 0);
       uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
-      // Pooled threshold.  The corpus is cut into n_pool = (#virtual slabs x G) disjoint PARTS: part (v, g) = the rows
-      // of virtual slab v that sit in column group g of their tile.  All virtual slabs of a query block run
-      // concurrently and publish the running MAXIMUM of each of their parts in gslab[part][q].  If every part has a
-      // row scoring >= x the corpus has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound
-      // of the global kk-th best -- and far tighter than any local bound while the lists warm up.
-      const int vslab = slab * ng + grp;
-      volatile uint32_t* gs = p.gslab + size_t(vslab) * G * p.q_stride + (live ? q : 0);
-      float pm[GMAX];
-#pragma unroll
-      for (int i = 0; i < GMAX; ++i) pm[i] = -INFINITY;
-      auto pm_fold = [&](int g, float v) {   // pm[g] = max(pm[g], v) for a runtime g, registers only
-#pragma unroll
-        for (int i = 0; i < GMAX; ++i) pm[i] = (g == i) ? fmaxf(pm[i], v) : pm[i];
-      };
+      // Pooled threshold.  The corpus is cut into n_pool = (#slabs x G) disjoint PARTS: part (v, g) = the rows of slab
+      // v that sit in column group g of their tile.  All slabs of a query block run concurrently and publish the
+      // running MAXIMUM of each of their parts in gslab[part][q].  If every part has a row scoring >= x the corpus
+      // has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound of the global kk-th best --
+      // and far tighter than any local bound while the lists warm up.
+      uint32_t* gs = p.gslab + size_t(slab) * G * p.q_stride + (live ? q : 0);
       float tau_pool = -INFINITY;
-      float tau_loc = -INFINITY;
       auto refresh_pool = [&]() {
         if (live) {
           uint32_t mn = 0xffffffffu;
@@ -293,22 +293,22 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           nB = make_float4(v[4], v[5], v[6], v[7]);
         }
       };
-      const int t_first = (ng == 1) ? t0 : t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of the item
+      const int t_first = t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of the item
       // Seed rendezvous (pooling only): every epilogue warp working on this block of 128 queries counts itself in
       // once its first tile's part maxima are published (or at once if it has no tile / cannot seed).
-      const uint32_t seed_expect = uint32_t(p.n_slabs * ng * 4);
+      const uint32_t seed_expect = uint32_t(p.n_slabs * 8);
       uint32_t* seed_ctr = p.seed_cnt + qb;
       const bool seeding = G > 0 && p.mask == nullptr && !(p.debug & 16);
       if (seeding && t_first >= t1 && lane == 0) atomicAdd(seed_ctr, 1u);
       load_norms(t_first);
       int nt = 0, next_refresh = 1;
-      for (int t = t_first; t < t1; t += ng, ++nt) {
+      for (int t = t_first; t < t1; t += 2, ++nt) {
         const uint32_t itt = it + uint32_t(t - t0);      // this tile's global sequence number
         __syncwarp();                                    // everyone is done reading the previous tile's strip
         sts_f32x4(nstrip + 32 * lane, nA);
         sts_f32x4(nstrip + 32 * lane + 16, nB);
         __syncwarp();
-        load_norms(t + ng);                              // prefetch for my next tile
+        load_norms(t + 2);                               // prefetch for my next tile
         // the pooled bound moves fastest early on: refreshed before tiles 1, 2, 3, 4, 6, 9, 13, ... then every 32nd
         if (G > 0 && nt == next_refresh) {
           refresh_pool();
@@ -320,9 +320,9 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t taddr0 = tmem_base + lane_addr + as * TILE_N;
         if (seeding && nt == 0) {
           // ---- seed pass over my FIRST tile: nothing is inserted; the maximum of each of its 8 sub-chunks of 32
-          // columns is folded into the G part maxima and published, then the warp waits (bounded) until every
-          // virtual slab of this query block has done the same.  The first real pass then starts from a threshold
-          // that only ~kk / (rows seen by all slabs) of the scores reach, instead of from -infinity.
+          // columns is folded into the part maxima and published, then the warp waits (bounded) until every slab
+          // of this query block has done the same.  The first real pass then starts from a threshold that only
+          // ~kk / (rows seen by all slabs) of the scores reach, instead of from -infinity.
           if (int64_t(t + 1) * TILE_N <= p.n_rows) {   // (a ragged tile has padding rows: it cannot seed)
 #pragma unroll 1
             for (int ch = 0; ch < TILE_N / 64; ++ch) {
@@ -344,14 +344,11 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                                    fmaxf(__uint_as_float(acc1[4 * g + 2]) * n.z, __uint_as_float(acc1[4 * g + 3]) * n.w)));
               }
               // column group of sub-chunk sc (32 columns): (sc * G) >> 3
-              pm_fold(((2 * ch) * G) >> 3, a);
-              pm_fold(((2 * ch + 1) * G) >> 3, b);
+              smem_atomic_max_u32(pm_addr + (((2 * ch) * G) >> 3) * 512, ord32(a));
+              smem_atomic_max_u32(pm_addr + (((2 * ch + 1) * G) >> 3) * 512, ord32(b));
             }
-            if (live) {
-#pragma unroll
-              for (int i = 0; i < GMAX; ++i)
-                if (i < G) gs[size_t(i) * p.q_stride] = ord32(pm[i]);
-            }
+            if (live)
+              for (int g = 0; g < G; ++g) atomicMax(gs + size_t(g) * p.q_stride, lds_u32_volatile(pm_addr + g * 512));
           }
           __threadfence();
           __syncwarp();
@@ -369,6 +366,8 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             refresh_pool();
           }
         }
+        const uint64_t root0 = lds_u64_volatile(st_root);   // the shared list's current root
+        float tau_loc = root0 ? key_score(root0) : -INFINITY;
         float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
         if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);   // lands while this tile is processed
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -380,7 +379,7 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // Survivors of pass 1 are taken out of the REGISTERS the accumulator chunk was loaded into: every lane
         // that has flagged columns picks ITS OWN lowest one through a select tree, so a round serves up to 32
         // different columns at once and a chunk costs max-over-lanes(#flagged) rounds, not #distinct columns.
-        // A survivor is first parked in a four-entry register stash; the heap work happens in ONE place (the drain
+        // A survivor is first parked in a four-entry register stash; the list work happens in ONE place (the drain
         // at the bottom of the loop: the list code is large, and inlined at several sites it overflowed the
         // instruction cache), when some lane's stash is full or the tile is done.  Iteration TILE_N/64 of the
         // chunk loop only drains.
@@ -450,25 +449,37 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 const int64_t row = int64_t(t) * TILE_N + j;
                 if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
                   const uint64_t key = make_key(s, uint32_t(row));
-                  const bool filling = cnt < p.kk;
-                  if (filling || key > root) {
-                    if (p.debug & 8) {   // timing experiment: no list work at all
-                      root = key;
-                    } else if (filling) {
-                      sts_u64(mylist + cnt * LSTRIDE, key);
-                      if (++cnt == p.kk) root = heap_build(mylist, p.kk);
-                    } else {
-                      root = heap_replace_root(mylist, p.kk, key);
-                    }
+                  // unlocked pre-check: the root only grows, so a key at or below a stale root is out for good
+                  if (lds_u32_volatile(st_cnt) < uint32_t(p.kk) || key > lds_u64_volatile(st_root)) {
+                    uint64_t root = 0;
+                    bool done = false;
+                    do {   // (the critical section sits INSIDE the retry loop: no lane waits while holding a lock)
+                      if (smem_try_lock(st_lock)) {
+                        const uint32_t cnt = lds_u32_volatile(st_cnt);
+                        root = lds_u64_volatile(st_root);
+                        if (p.debug & 8) {   // timing experiment: no list work at all
+                          root = key;
+                          sts_u64(st_root, root);
+                        } else if (cnt < uint32_t(p.kk)) {
+                          sts_u64(mylist + cnt * LSTRIDE, key);
+                          sts_u32(st_cnt, cnt + 1);
+                          if (cnt + 1 == uint32_t(p.kk)) {
+                            root = heap_build(mylist, p.kk);
+                            sts_u64(st_root, root);
+                          }
+                        } else if (key > root) {
+                          root = heap_replace_root(mylist, p.kk, key);
+                          sts_u64(st_root, root);
+                        }
+                        smem_unlock(st_lock);
+                        done = true;
+                      }
+                    } while (!done);
                     if (G > 0) {   // running maximum of the row's pool part
                       const int g = ((j >> 5) * G) >> 3;
-                      float cur = pm[0];
-#pragma unroll
-                      for (int i = 1; i < GMAX; ++i) cur = (g == i) ? pm[i] : cur;
-                      if (s > cur) {
-                        pm_fold(g, s);
-                        if (!(p.debug & 4)) gs[size_t(g) * p.q_stride] = ord32(s);
-                      }
+                      const uint32_t o = ord32(s);
+                      if (o > smem_atomic_max_u32(pm_addr + g * 512, o) && !(p.debug & 4))
+                        atomicMax(gs + size_t(g) * p.q_stride, o);
                     }
                     if (root) {
                       tau_loc = key_score(root);
@@ -489,11 +500,13 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
       it += uint32_t(t1 - t0);
-      // ---- hand the list over
+      // ---- hand the list over: both groups are done with it, each writes every other slot
+      named_bar_sync(EPI_BAR, 256);
       if (qb < p.nqb) {   // (the odd block out of a pair carries no queries)
-        uint64_t* dst = p.parts + (size_t(vslab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
-        for (int c = 0; c < p.kk; ++c) dst[c] = lds_u64(mylist + c * LSTRIDE);
+        uint64_t* dst = p.parts + (size_t(slab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
+        for (int c = grp; c < p.kk; c += 2) dst[c] = lds_u64(mylist + c * LSTRIDE);
       }
+      named_bar_sync(EPI_BAR, 256);   // ... before the next item's list is zeroed
     }
   }
 
@@ -560,13 +573,14 @@ static bool cached_map(const void* ptr, int64_t rows, int dim, CUtensorMap& out)
 }
 
 struct Plan {
-  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, pool_g, n_groups;
+  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, pool_g;
   size_t smem;
 };
 
-static size_t smem_bytes(int n_groups, int kk, int n_stages) {
-  return 1024 /*align*/ + size_t(n_stages) * STAGE_BYTES + size_t(n_groups) * kk * BLOCK_M * 8 +
-         size_t(4 * n_groups) * TILE_N * 4 + (2 * size_t(MAX_STAGES) + 4) * 8 + 64;
+static size_t smem_bytes(int kk, int n_stages, int pool_g) {
+  return 1024 /*align*/ + size_t(n_stages) * STAGE_BYTES + size_t(kk) * BLOCK_M * 8 /*list*/ + BLOCK_M * 16 /*state*/ +
+         size_t(pool_g) * BLOCK_M * 4 /*part maxima*/ + 8 * TILE_N * 4 /*norm strips*/ +
+         (2 * size_t(MAX_STAGES) + 4) * 8 + 64;
 }
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
@@ -574,17 +588,6 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   if (n_queries <= 0 || n_rows <= 0 || n_rows >= (int64_t(1) << 31)) return false;
   const int g = sm_count();
   if (g < 2) return false;
-  // two heaps per query (two epilogue groups) when four ring stages still fit; else one group and >= 2 stages
-  static const int want_groups = [] { const char* e = getenv("DRS_PAIR_GROUPS"); return e ? atoi(e) : 0; }();   // tuning hook
-  pl.n_groups = 2;
-  if (want_groups == 1 || smem_bytes(2, kk, 4) > SMEM_LIMIT) pl.n_groups = 1;
-  if (smem_bytes(pl.n_groups, kk, 2) > SMEM_LIMIT) return false;
-  int ns = 2;
-  while (ns < MAX_STAGES && smem_bytes(pl.n_groups, kk, ns + 1) <= SMEM_LIMIT) ++ns;
-  static const int cap_stages = [] { const char* e = getenv("DRS_PAIR_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
-  if (cap_stages >= 2 && ns > cap_stages) ns = cap_stages;
-  pl.n_stages = ns;
-  pl.smem = smem_bytes(pl.n_groups, kk, ns);
   pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
   pl.nqb2 = (pl.nqb + 1) / 2;
   pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
@@ -596,16 +599,22 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   pl.n_slabs = s < 1 ? 1 : s;
   const int items = pl.nqb2 * pl.n_slabs;
   pl.grid = 2 * (items < gp ? items : gp);
-  // pool parts: the smallest G in {1, 2, 4, 8} with (#virtual slabs x G) >= kk; pooling needs every virtual slab of
-  // a query block resident at the same time (one item per pair)
-  const int nv = pl.n_groups * pl.n_slabs;
+  // pool parts: the smallest G in {1, 2, 4, 8} with (#slabs x G) >= kk; pooling needs every slab of a query block
+  // resident at the same time (one item per pair)
   pl.pool_g = 0;
   if (items <= gp)
-    for (int g = 1; g <= (pl.n_groups == 2 ? 2 : 8); g <<= 1)
-      if (nv * g >= kk) {
-        pl.pool_g = g;
+    for (int pg = 1; pg <= POOL_GMAX; pg <<= 1)
+      if (pl.n_slabs * pg >= kk) {
+        pl.pool_g = pg;
         break;
       }
+  if (smem_bytes(kk, 2, pl.pool_g) > SMEM_LIMIT) return false;
+  int ns = 2;
+  while (ns < MAX_STAGES && smem_bytes(kk, ns + 1, pl.pool_g) <= SMEM_LIMIT) ++ns;
+  static const int cap_stages = [] { const char* e = getenv("DRS_PAIR_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
+  if (cap_stages >= 2 && ns > cap_stages) ns = cap_stages;
+  pl.n_stages = ns;
+  pl.smem = smem_bytes(kk, ns, pl.pool_g);
   return true;
 }
 
@@ -619,19 +628,19 @@ bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk) {
 
 int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk) {
   umma::ss2::Plan pl;
-  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs : 0;
+  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs : 0;
 }
 
 // pool parts (rows of the per-part threshold table right after gtau[q_stride]) and the u32 words of the whole
 // zero-initialised threshold area: gtau[q_stride] | gslab[pool parts][q_stride] | seed counters
 int dense_pair_pool_parts(int n_queries, int64_t n_rows, int dim, int kk) {
   umma::ss2::Plan pl;
-  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_groups * pl.n_slabs * pl.pool_g : 0;
+  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs * pl.pool_g : 0;
 }
 size_t dense_pair_threshold_words(int n_queries, int64_t n_rows, int dim, int kk, int q_stride) {
   umma::ss2::Plan pl;
   if (!umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl)) return 0;
-  return size_t(q_stride) * (1 + size_t(pl.n_groups) * pl.n_slabs * pl.pool_g) + 2 * size_t(pl.nqb2) + 8;
+  return size_t(q_stride) * (1 + size_t(pl.n_slabs) * pl.pool_g) + 2 * size_t(pl.nqb2) + 8;
 }
 
 // rows of the bf16 query image the kernel reads through TMA (workspace: rows * dim * 2 bytes, 128-byte aligned)
@@ -657,7 +666,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   p.parts = d_parts;
   p.gtau = d_gtau;
   p.gslab = d_gtau + q_stride;
-  p.seed_cnt = d_gtau + size_t(q_stride) * (1 + size_t(pl.n_groups) * pl.n_slabs * pl.pool_g);
+  p.seed_cnt = d_gtau + size_t(q_stride) * (1 + size_t(pl.n_slabs) * pl.pool_g);
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -669,7 +678,6 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_tiles = pl.n_tiles;
   p.n_stages = pl.n_stages;
   p.pool_g = pl.pool_g;
-  p.n_groups = pl.n_groups;
   static const uint32_t dbg = [] { const char* e = getenv("DRS_PAIR_DEBUG"); return e ? uint32_t(atoi(e)) : 0u; }();
   p.debug = dbg;
   // DRS_PAIR_TRACE=1 (debugging aid, synchronises): per-tile timeline of one epilogue warp on stderr
@@ -681,9 +689,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   static std::once_flag attr_once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(dense_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
-    if (attr_rc == cudaSuccess)
-      attr_rc = cudaFuncSetAttribute(dense_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
+    attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
   });
   DRS_CUDA_CHECK(attr_rc);
   DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, dense_pair_threshold_words(n_queries, n_rows, dim, kk, q_stride) * sizeof(uint32_t), st));
@@ -695,7 +701,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pl.grid);
-  cfg.blockDim = dim3(128 + 128 * pl.n_groups);
+  cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -705,16 +711,15 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (pl.n_groups == 2) DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel<2>, tmap_q, tmap_c, p));
-  else DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel<1>, tmap_q, tmap_c, p));
+  DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dense_pair_kernel, tmap_q, tmap_c, p));
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   if (want_trace) {
     static unsigned long long h[3000];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pair trace] tiles/slab %d groups %d stages %d pool_g %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
-            pl.n_tiles / pl.n_slabs, pl.n_groups, pl.n_stages, pl.pool_g);
+    fprintf(stderr, "[pair trace] tiles/slab %d stages %d pool_g %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
+            pl.n_tiles / pl.n_slabs, pl.n_stages, pl.pool_g);
     for (int i = 0; i < 1000 && h[3 * i + 1]; ++i)
       fprintf(stderr, "[pair trace] %d %llu %llu %llu\n", i, h[3 * i] - h[0], h[3 * i + 1] - h[3 * i], h[3 * i + 2]);
   }

@@ -209,6 +209,36 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32x4(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// ---- shared-memory atomics / ordered accesses by 32-bit shared address (per-lane locks, shared maxima)
+__device__ __forceinline__ bool smem_try_lock(uint32_t addr) {
+  uint32_t old;
+  asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(addr) : "memory");
+  return old == 0u;
+}
+__device__ __forceinline__ void smem_unlock(uint32_t addr) {
+  asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_atomic_max_u32(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.relaxed.cta.shared.max.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t lds_u64_volatile(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t v;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
