@@ -98,8 +98,9 @@ static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim,
 }
 
 struct DenseWs {
-  size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, qimg_off, total;
+  size_t parts_keys, cand_keys, scratch_keys, flags_off, gtau_off, qimg_off, counts_off, ovf_off, total;
   int simt_parts, umma_parts, umma_qstride, variant, pool_parts;
+  DensePairGeometry geo;
 };
 
 static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
@@ -108,24 +109,27 @@ static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int 
   const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
   w.simt_parts = dense_simt_grid();
   w.variant = (which == DRS_DENSE_UMMA) ? tensor_variant(kernel, n_queries, n_rows, dim, int(kk)) : TENSOR_NONE;
-  w.umma_parts = w.variant == TENSOR_PAIR ? dense_pair_parts(n_queries, n_rows, dim, int(kk))
-                                          : (w.variant == TENSOR_TS ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0);
   w.umma_qstride = ((n_queries + 127) / 128) * 128;
+  w.umma_parts = w.variant == TENSOR_TS ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0;
+  size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk, thr_words = size_t(w.umma_qstride) * (1 + size_t(w.umma_parts));
+  w.pool_parts = w.umma_parts;
+  if (w.variant == TENSOR_PAIR && dense_pair_geometry(n_queries, n_rows, dim, int(kk), w.umma_qstride, w.geo)) {
+    umma_keys = size_t(w.geo.n_slabs) * w.umma_qstride * w.geo.cap;   // one append buffer per (slab, query)
+    thr_words = w.geo.zero_words;
+    w.pool_parts = w.geo.pool_parts;
+  }
   const size_t simt_keys = size_t(w.simt_parts) * n_queries * kk;
-  const size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk;
   w.parts_keys = std::max(simt_keys, umma_keys);
   w.cand_keys = size_t(n_queries) * kk;
   w.scratch_keys = std::max(merge_scratch_keys(w.simt_parts, n_queries, int(kk)),
                             merge_scratch_keys(w.umma_parts, n_queries, int(kk)));
   w.flags_off = (w.parts_keys + w.cand_keys + w.scratch_keys) * 8;
   w.gtau_off = w.flags_off + ((size_t(n_queries) * 4 + 255) / 256) * 256;
-  // bf16 image of the queries (the pair kernel's TMA source), 128-byte aligned
-  w.pool_parts = w.variant == TENSOR_PAIR ? dense_pair_pool_parts(n_queries, n_rows, dim, int(kk)) : w.umma_parts;
-  const size_t thr_words = w.variant == TENSOR_PAIR
-                               ? dense_pair_threshold_words(n_queries, n_rows, dim, int(kk), w.umma_qstride)
-                               : size_t(w.umma_qstride) * (1 + size_t(w.umma_parts));
+  // pair kernel: bf16 image of the queries (its TMA source, 128-byte aligned), append counts, overflow marks
   w.qimg_off = ((w.gtau_off + thr_words * 4 + 255) / 256) * 256;
-  w.total = w.qimg_off + (w.variant == TENSOR_PAIR ? size_t(dense_pair_query_rows(n_queries)) * dim * 2 : 0) + 256;
+  w.counts_off = w.qimg_off + (w.variant == TENSOR_PAIR ? size_t(w.geo.query_rows) * dim * 2 : 0);
+  w.ovf_off = w.counts_off + (w.variant == TENSOR_PAIR ? size_t(w.geo.n_slabs) * w.umma_qstride * 4 : 0);
+  w.total = w.ovf_off + (w.variant == TENSOR_PAIR ? size_t(w.umma_qstride) * 4 : 0) + 256;
   return w;
 }
 
@@ -206,27 +210,38 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
     return launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk_s, kprime, 4e-6f,
                                 d_out_scores, d_out_ids, flags, nullptr, DRS_QMODE_EXACT, 1, 0, st);
   }
-  {
-    ProfScope ps(DRS_PROF_DENSE_SELECT, st);
-    uint32_t* gtau = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off);
-    if (w.variant == TENSOR_PAIR)
+  uint8_t* ws8 = reinterpret_cast<uint8_t*>(d_workspace);
+  uint32_t* gtau = reinterpret_cast<uint32_t*>(ws8 + w.gtau_off);
+  if (w.variant == TENSOR_PAIR) {
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws8 + w.counts_off);
+    int32_t* ovf = reinterpret_cast<int32_t*>(ws8 + w.ovf_off);
+    {
+      ProfScope ps(DRS_PROF_DENSE_SELECT, st);
       rc = launch_dense_pair(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
-                             w.umma_qstride, gtau, reinterpret_cast<uint8_t*>(d_workspace) + w.qimg_off, st);
-    else
+                             counts, w.umma_qstride, gtau, ws8 + w.qimg_off, st);
+    }
+    if (rc != DRS_OK) return rc;
+    ProfScope pt(DRS_PROF_DENSE_TAIL, st);
+    rc = launch_merge_appended(parts, counts, w.geo.n_slabs, w.umma_qstride, w.geo.cap, n_queries, kk, cand, gtau,
+                               w.geo.pool_parts, ovf, st);
+    if (rc != DRS_OK) return rc;
+    rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
+                              d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st, ovf);
+  } else {
+    {
+      ProfScope ps(DRS_PROF_DENSE_SELECT, st);
       rc = launch_dense_umma(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk, parts,
                              w.umma_qstride, gtau, st);
-  }
-  if (rc != DRS_OK) return rc;
-  ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-  {
+    }
+    if (rc != DRS_OK) return rc;
+    ProfScope pt(DRS_PROF_DENSE_TAIL, st);
     // the kernel's own thresholds (gtau, and the per-slab pooled bounds when pooling was on) pre-filter the merge
-    const uint32_t* gtau = reinterpret_cast<const uint32_t*>(reinterpret_cast<uint8_t*>(d_workspace) + w.gtau_off);
     rc = launch_merge_keys_filtered(parts, w.umma_parts, w.umma_qstride, n_queries, kk, cand, nullptr, scratch, gtau,
                                     gtau + w.umma_qstride, w.pool_parts, w.umma_qstride, st);
+    if (rc != DRS_OK) return rc;
+    rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
+                              d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st);
   }
-  if (rc != DRS_OK) return rc;
-  rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
-                            d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st);
   if (rc != DRS_OK || !escalate) return rc;
   // Re-run the (few) queries whose tensor-core result is not proven exact through the fp32 kernel.
   // Everything is predicated on flags[] on the device; with no flagged query the kernels exit at once.

@@ -152,7 +152,7 @@ int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, 
                          int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
                          const int32_t* d_active, int query_mode, int flag_unproven, int flag_proven,
-                         cudaStream_t st);
+                         cudaStream_t st, const int32_t* d_force_unproven = nullptr);
 int launch_merge_pairs_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries, int k, int k_out,
                            double* d_out_scores, int64_t* d_out_ids, int32_t* d_flags, cudaStream_t st);
 // dense_simt.cu
@@ -169,13 +169,18 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
                       int q_stride, uint32_t* d_gtau, cudaStream_t st);
 
 // dense_pair.cu
+struct DensePairGeometry {
+  int n_slabs, cap, pool_parts, query_rows;
+  size_t zero_words;
+};
 bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk);
-int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk);
-int dense_pair_query_rows(int n_queries);
-int dense_pair_pool_parts(int n_queries, int64_t n_rows, int dim, int kk);
-size_t dense_pair_threshold_words(int n_queries, int64_t n_rows, int dim, int kk, int q_stride);
+bool dense_pair_geometry(int n_queries, int64_t n_rows, int dim, int kk, int q_stride, DensePairGeometry& geo);
 int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
-                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts,
-                      int q_stride, uint32_t* d_gtau, void* d_qbf16, cudaStream_t st);
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, uint32_t* d_counts,
+                      int q_stride, uint32_t* d_zero_area, void* d_qbf16, cudaStream_t st);
+// select.cu: top-kk of the keys the pair kernel appended (filtered by its final thresholds); overflow marks
+int launch_merge_appended(const uint64_t* d_parts, const uint32_t* d_counts, int n_slabs, int q_stride, int cap,
+                          int n_queries, int kk, uint64_t* d_out, const uint32_t* d_pool, int n_pool,
+                          int32_t* d_overflow, cudaStream_t st);
 
 }  // namespace drs

@@ -12,14 +12,19 @@
 //   D          = 2 x (128 lanes x 256 columns) fp32 in tensor memory: ALL 512 columns, double buffered, so the
 //                epilogue of tile t overlaps the MMAs of tile t+1.
 //   epilogue   = lane L of a CTA is query L of its block; after tcgen05.ld a thread holds its query's 256 scores of the
-//                tile, scales them by inv_norm[row] and compares against its threshold; the rare survivors go to the
-//                query's min-heap in shared memory.  Never writes scores.
+//                tile, scales them by inv_norm[row] and compares against its threshold -- a proven lower bound of
+//                the query's kk-th best score over the whole corpus, shared by all CTAs (see "pool parts").  The rare
+//                survivors are APPENDED to the query's candidate buffer in global memory: no list, no heap and no
+//                score is ever kept on chip, so shared memory is all ring, and k' is not limited by it.
 //
 // Roles per CTA (384 threads): warp 0 TMA producer (each CTA loads ITS halves), warp 1 MMA issuer (leader CTA only,
-// one elected lane), warp 2 tensor-memory allocator, warps 4..11 two epilogue groups that alternate tiles and share
-// ONE candidate list per query (per-lane lock).  Work item = (pair of query blocks, slab of corpus tiles); the pairs that run
-// concurrently cover the same slab for different query blocks, so the corpus leaves HBM about once.
-// Output: one partial list of kk keys per (virtual slab, query); merged and exactly re-scored downstream (select.cu).
+// one elected lane), warp 2 tensor-memory allocator, warps 4..11 two epilogue groups that alternate tiles.
+// Work item = (pair of query blocks, slab of corpus tiles), ONE per CTA pair (the threshold scheme needs every slab
+// of a query block resident at once); the pairs that run concurrently cover the same slab for different query
+// blocks, so the corpus leaves HBM about once.
+// Output: per (slab, query) the appended keys and their count; select.cu drops what the final thresholds rule out,
+// keeps the kk best and re-scores them exactly.  A buffer that overflows (thresholds that cannot tighten: e.g. an
+// all-zero query, every score ties) marks its query "unproven", which sends it through the exact fp32 kernel.
 #include <cuda.h>
 
 #include <cstdio>
@@ -49,17 +54,18 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(TILE_N
 struct Params {
   const float* inv_norm;
   const uint8_t* mask;
-  uint64_t* parts;
-  uint32_t* gtau;    // [q_stride] zero-initialised shared thresholds
-  uint32_t* gslab;   // [n_slabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
-  uint32_t* seed_cnt;// [2 * nqb2] zero-initialised: epilogue warps of a query block that are past their seed pass
+  uint64_t* parts;     // [n_slabs][q_stride][cap] appended keys
+  uint32_t* counts;    // [n_slabs][q_stride] keys appended (may exceed cap: the excess was dropped = overflow)
+  uint32_t* gslab;     // [n_slabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
+  uint32_t* seed_cnt;  // [2 * nqb2] zero-initialised: epilogue warps of a query block that are past their seed pass
   int64_t n_rows;
-  int n_queries, nqb, nqb2, dim, kk, q_stride, n_slabs, n_tiles, n_stages;
-  int pool_g;        // pool parts per slab (1, 2, 4, 8: column groups of a tile), 0 = pooling off
-  uint32_t debug;    // timing experiments only (results are garbage): 1 no inserts, 2 no epilogue work,
-                     // 4 no threshold publishing, 8 no list work
+  int n_queries, nqb, nqb2, dim, kk, cap, q_stride, n_slabs, n_tiles, n_stages;
+  int pool_g;          // pool parts per slab (1, 2, .. 32: groups of 256 / pool_g columns of a tile)
+  int mask_vec;        // the row mask may be read 8 bytes at a time (8-byte aligned)
+  uint32_t debug;      // timing experiments only (results are garbage): 1 no survivors, 2 no epilogue work,
+                       // 4 no threshold publishing, 16 no seed pass
   unsigned long long* trace;   // DRS_PAIR_TRACE: per tile of block 0 / warp 4: {clock at accumulator ready, clock at
-                               // tile done, flagged columns}; NULL otherwise
+                               // tile done, drains}; NULL otherwise
 };
 
 // D[tmem, 256 x 256 over the pair] (+)= A[smem, 128 rows per CTA] * B[smem, 128 rows per CTA]^T
@@ -96,8 +102,9 @@ __global__ void __launch_bounds__(256) queries_to_bf16_kernel(const float* __res
 }
 
 constexpr int THREADS = 384;                         // 4 service warps + 2 epilogue groups of 4 warps
-constexpr int POOL_GMAX = 8;                         // pool parts per slab at most (column groups of a tile)
+constexpr int POOL_GMAX = 32;                        // pool parts per slab at most (groups of 8 columns of a tile)
 constexpr int EPI_BAR = 1;                           // named barrier of the 8 epilogue warps
+constexpr int STRIP_WORDS = TILE_N + 8;              // per warp: the tile's 256 inverse norms + 256 validity bits
 
 __global__ void __launch_bounds__(THREADS, 1)
 dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c, Params p) {
@@ -105,14 +112,13 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int cta = int(blockIdx.x >> 1);               // work-item stream this pair walks
   const int n_ctas = int(gridDim.x >> 1);
   extern __shared__ uint8_t smem_dyn[];
-  // carve: [ring | list | lane state | part maxima | norm strips | barriers | tmem slot]; the swizzled ring needs
+  // carve: [ring | append counters | part maxima | norm strips | barriers | tmem slot]; the swizzled ring needs
   // 1024-byte alignment
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);        // [kk][128] keys
-  uint8_t* lstate = reinterpret_cast<uint8_t*>(lists + size_t(p.kk) * BLOCK_M);                  // [128] {root, cnt, lock}
-  uint32_t* pmem = reinterpret_cast<uint32_t*>(lstate + BLOCK_M * 16);                            // [pool_g][128] ord32
-  float* norm_strips = reinterpret_cast<float*>(pmem + size_t(p.pool_g) * BLOCK_M);              // [8 warps][TILE_N]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_strips + 8 * TILE_N);
+  uint32_t* acnt = reinterpret_cast<uint32_t*>(ring + size_t(p.n_stages) * STAGE_BYTES);   // [128] keys appended
+  uint32_t* pmem = acnt + BLOCK_M;                                                           // [pool_g][128] ord32
+  float* norm_strips = reinterpret_cast<float*>(pmem + size_t(p.pool_g) * BLOCK_M);         // [8 warps][STRIP_WORDS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(norm_strips + 8 * STRIP_WORDS);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.n_stages;
   uint64_t* tfull = bars + 2 * p.n_stages;
@@ -226,18 +232,15 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else if (warp >= 4) {
     // ===================================================================== epilogue
     // Two groups of four warps; group g owns accumulator stage g and every other tile, i.e. has two tile-times to
-    // drain one tile.  Lane L of BOTH groups is query L of the block: the two threads share ONE candidate list
-    // (and its state: root, fill count, part maxima) in shared memory, guarded by a per-lane lock -- survivors are
-    // rare, so the lock is almost never contended, and the list memory of a second heap buys ring stages instead.
+    // drain one tile.  Lane L of BOTH groups is query L of the block.
     const int ew = warp & 3;                 // the TMEM sub-partition (lanes 32*ew ..) this warp may touch
     const int grp = (warp - 4) >> 2;
     const int L = ew * 32 + lane;            // TMEM lane == query within my block
     const uint32_t lane_addr = uint32_t(ew * 32) << 16;
-    const uint32_t mylist = smem_u32(lists) + uint32_t(L) * 8;          // slot 0 of lane L's list
-    const uint32_t st_root = smem_u32(lstate) + uint32_t(L) * 16;       // u64 root (0 until the list is a heap)
-    const uint32_t st_cnt = st_root + 8, st_lock = st_root + 12;        // u32 entries while filling, u32 lock
+    const uint32_t cnt_addr = smem_u32(acnt) + uint32_t(L) * 4;         // keys appended for query L (both groups)
     const uint32_t pm_addr = smem_u32(pmem) + uint32_t(L) * 4;          // part g at + g * 512
-    const uint32_t nstrip = smem_u32(norm_strips + (warp - 4) * TILE_N);   // this warp's norm strip
+    const uint32_t nstrip = smem_u32(norm_strips + (warp - 4) * STRIP_WORDS);   // this warp's norm strip ...
+    const uint32_t vstrip = nstrip + TILE_N * 4;                                // ... and row validity bits
     const uint32_t tempty_leader = mapa_u32(smem_u32(tempty), 0);
     const bool no_insert = (p.debug & 1) != 0;
     const int G = p.pool_g;
@@ -249,56 +252,71 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       slab_tiles(slab, t0, t1);
       const int q = qb * BLOCK_M + L;
       const bool live = q < p.n_queries;
-      // The list fills by plain appends (cnt < kk), is turned into a min-heap once (Floyd), and from then on its
-      // root is the kk-th best candidate: replacing it costs O(log kk).
       if (grp == 0) {
-        for (int c = 0; c < p.kk; ++c) sts_u64(mylist + c * LSTRIDE, 0);
-        sts_u64(st_root, 0);
-        sts_u64(st_cnt, 0);   // cnt and lock
+        sts_u32(cnt_addr, 0u);
         for (int g = 0; g < G; ++g) sts_u32(pm_addr + g * 512, 0u);
       }
       named_bar_sync(EPI_BAR, 256);
-      // gtau[q]: a lower bound on query q's kk-th best score over the WHOLE corpus, published by every list working
-      // on q (ordered-u32 image, atomicMax).  Padding lanes never insert.
-      uint32_t* gt = p.gtau + (live ? q : 0);
-      uint32_t g_seen = live ? *reinterpret_cast<volatile uint32_t*>(gt) : 0u;
-      // Pooled threshold.  The corpus is cut into n_pool = (#slabs x G) disjoint PARTS: part (v, g) = the rows of slab
-      // v that sit in column group g of their tile.  All slabs of a query block run concurrently and publish the
-      // running MAXIMUM of each of their parts in gslab[part][q].  If every part has a row scoring >= x the corpus
-      // has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound of the global kk-th best --
-      // and far tighter than any local bound while the lists warm up.
+      uint64_t* mybuf = p.parts + (size_t(slab) * p.q_stride + (live ? q : 0)) * p.cap;
+      // Pool parts.  The corpus is cut into n_pool = (#slabs x G) disjoint PARTS: part (v, g) = the rows of slab v
+      // that sit in column group g (256 / G columns) of their tile.  All slabs of a query block run concurrently
+      // and publish the running MAXIMUM of each of their parts in gslab[part][q].  If every part has a row scoring
+      // >= x the corpus has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound of the
+      // global kk-th best: a row scoring below it can be dropped for good.
       uint32_t* gs = p.gslab + size_t(slab) * G * p.q_stride + (live ? q : 0);
-      float tau_pool = -INFINITY;
+      float tau = live ? -INFINITY : INFINITY;   // padding lanes never survive
       auto refresh_pool = [&]() {
         if (live) {
           uint32_t mn = 0xffffffffu;
           const volatile uint32_t* col = p.gslab + q;
           for (int sl = 0; sl < n_pool; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
-          if (mn != 0u) tau_pool = fmaxf(tau_pool, unord32(mn));   // 0 = some part has not reported yet
+          if (mn != 0u) tau = fmaxf(tau, unord32(mn));   // 0 = some part has not reported yet
         }
       };
-      // inverse norms of the tile's 256 rows: lane l fetches rows 8l..8l+7 one tile ahead, parks them in this warp's
-      // strip, and every lane reads all of them by broadcast
+      // inverse norms and validity (inside the corpus, passes the row mask) of the tile's 256 rows: lane l fetches
+      // rows 8l..8l+7 one tile ahead, parks them in this warp's strip, and every lane reads all of them by broadcast
       float4 nA, nB;
+      uint32_t vbyte;
       auto load_norms = [&](int t) {
         const int64_t r = int64_t(t) * TILE_N + 8 * lane;
         if (t < t1 && r + 7 < p.n_rows) {
           nA = __ldg(reinterpret_cast<const float4*>(p.inv_norm + r));
           nB = __ldg(reinterpret_cast<const float4*>(p.inv_norm + r + 4));
+          vbyte = 0xffu;
+          if (p.mask != nullptr) {
+            uint2 mk;
+            if (p.mask_vec) {
+              mk = __ldg(reinterpret_cast<const uint2*>(p.mask + r));
+            } else {
+              mk.x = uint32_t(p.mask[r]) | (uint32_t(p.mask[r + 1]) << 8) | (uint32_t(p.mask[r + 2]) << 16) | (uint32_t(p.mask[r + 3]) << 24);
+              mk.y = uint32_t(p.mask[r + 4]) | (uint32_t(p.mask[r + 5]) << 8) | (uint32_t(p.mask[r + 6]) << 16) | (uint32_t(p.mask[r + 7]) << 24);
+            }
+            vbyte = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              vbyte |= ((mk.x >> (8 * j)) & 0xffu) ? (1u << j) : 0u;
+              vbyte |= ((mk.y >> (8 * j)) & 0xffu) ? (16u << j) : 0u;
+            }
+          }
         } else {
           float v[8];
+          vbyte = 0u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (t < t1 && r + j < p.n_rows) ? __ldg(p.inv_norm + r + j) : 0.f;
+          for (int j = 0; j < 8; ++j) {
+            const bool in = t < t1 && r + j < p.n_rows;
+            v[j] = in ? __ldg(p.inv_norm + r + j) : 0.f;
+            if (in && (p.mask == nullptr || p.mask[r + j] != 0)) vbyte |= 1u << j;
+          }
           nA = make_float4(v[0], v[1], v[2], v[3]);
           nB = make_float4(v[4], v[5], v[6], v[7]);
         }
       };
       const int t_first = t0 + (((it & 1u) == uint32_t(grp)) ? 0 : 1);   // my first tile of the item
-      // Seed rendezvous (pooling only): every epilogue warp working on this block of 128 queries counts itself in
-      // once its first tile's part maxima are published (or at once if it has no tile / cannot seed).
+      // Seed rendezvous: every epilogue warp working on this block of 128 queries counts itself in once its first
+      // tile's part maxima are published (or at once if it has no tile / cannot seed).
       const uint32_t seed_expect = uint32_t(p.n_slabs * 8);
       uint32_t* seed_ctr = p.seed_cnt + qb;
-      const bool seeding = G > 0 && p.mask == nullptr && !(p.debug & 16);
+      const bool seeding = !(p.debug & 16);
       if (seeding && t_first >= t1 && lane == 0) atomicAdd(seed_ctr, 1u);
       load_norms(t_first);
       int nt = 0, next_refresh = 1;
@@ -307,10 +325,11 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         __syncwarp();                                    // everyone is done reading the previous tile's strip
         sts_f32x4(nstrip + 32 * lane, nA);
         sts_f32x4(nstrip + 32 * lane + 16, nB);
+        sts_u8(vstrip + lane, vbyte);
         __syncwarp();
         load_norms(t + 2);                               // prefetch for my next tile
-        // the pooled bound moves fastest early on: refreshed before tiles 1, 2, 3, 4, 6, 9, 13, ... then every 32nd
-        if (G > 0 && nt == next_refresh) {
+        // the bound moves fastest early on: refreshed before tiles 1, 2, 3, 4, 6, 9, 13, ... then every 32nd
+        if (nt == next_refresh) {
           refresh_pool();
           next_refresh += min(32, max(1, nt >> 1));
         }
@@ -319,33 +338,38 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         tc_fence_after();
         const uint32_t taddr0 = tmem_base + lane_addr + as * TILE_N;
         if (seeding && nt == 0) {
-          // ---- seed pass over my FIRST tile: nothing is inserted; the maximum of each of its 8 sub-chunks of 32
-          // columns is folded into the part maxima and published, then the warp waits (bounded) until every slab
-          // of this query block has done the same.  The first real pass then starts from a threshold that only
+          // ---- seed pass over my FIRST tile: nothing is appended; the maximum of each group of 8 columns is
+          // folded into the part maxima and published, then the warp waits (bounded) until every slab of this
+          // query block has done the same.  The first real pass then starts from a threshold that only
           // ~kk / (rows seen by all slabs) of the scores reach, instead of from -infinity.
-          if (int64_t(t + 1) * TILE_N <= p.n_rows) {   // (a ragged tile has padding rows: it cannot seed)
+          {
 #pragma unroll 1
             for (int ch = 0; ch < TILE_N / 64; ++ch) {
               uint32_t acc0[32], acc1[32];
               tmem_ld32(taddr0 + ch * 64, acc0);
               tmem_ld32(taddr0 + ch * 64 + 32, acc1);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-              float a = -INFINITY, b = -INFINITY;
+              const uint32_t vb0 = lds_u32_volatile(vstrip + 8 * ch), vb1 = lds_u32_volatile(vstrip + 8 * ch + 4);
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 n = lds_f32x4(nstrip + (ch * 64 + 4 * g) * 4);
-                a = fmaxf(a, fmaxf(fmaxf(__uint_as_float(acc0[4 * g + 0]) * n.x, __uint_as_float(acc0[4 * g + 1]) * n.y),
-                                   fmaxf(__uint_as_float(acc0[4 * g + 2]) * n.z, __uint_as_float(acc0[4 * g + 3]) * n.w)));
+              for (int g = 0; g < 4; ++g) {   // column group of columns c..c+7: ((c >> 3) * G) >> 5
+                const float4 n0 = lds_f32x4(nstrip + (ch * 64 + 8 * g) * 4), n1 = lds_f32x4(nstrip + (ch * 64 + 8 * g + 4) * 4);
+                const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                float a = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  a = fmaxf(a, ((vb0 >> (8 * g + e)) & 1u) ? __uint_as_float(acc0[8 * g + e]) * nn[e] : -INFINITY);
+                smem_atomic_max_u32(pm_addr + (((ch * 8 + g) * G) >> 5) * 512, ord32(a));
               }
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                const float4 n = lds_f32x4(nstrip + (ch * 64 + 32 + 4 * g) * 4);
-                b = fmaxf(b, fmaxf(fmaxf(__uint_as_float(acc1[4 * g + 0]) * n.x, __uint_as_float(acc1[4 * g + 1]) * n.y),
-                                   fmaxf(__uint_as_float(acc1[4 * g + 2]) * n.z, __uint_as_float(acc1[4 * g + 3]) * n.w)));
+              for (int g = 0; g < 4; ++g) {
+                const float4 n0 = lds_f32x4(nstrip + (ch * 64 + 32 + 8 * g) * 4), n1 = lds_f32x4(nstrip + (ch * 64 + 32 + 8 * g + 4) * 4);
+                const float nn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                float a = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                  a = fmaxf(a, ((vb1 >> (8 * g + e)) & 1u) ? __uint_as_float(acc1[8 * g + e]) * nn[e] : -INFINITY);
+                smem_atomic_max_u32(pm_addr + (((ch * 8 + 4 + g) * G) >> 5) * 512, ord32(a));
               }
-              // column group of sub-chunk sc (32 columns): (sc * G) >> 3
-              smem_atomic_max_u32(pm_addr + (((2 * ch) * G) >> 3) * 512, ord32(a));
-              smem_atomic_max_u32(pm_addr + (((2 * ch + 1) * G) >> 3) * 512, ord32(b));
             }
             if (live)
               for (int g = 0; g < G; ++g) atomicMax(gs + size_t(g) * p.q_stride, lds_u32_volatile(pm_addr + g * 512));
@@ -366,10 +390,6 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             refresh_pool();
           }
         }
-        const uint64_t root0 = lds_u64_volatile(st_root);   // the shared list's current root
-        float tau_loc = root0 ? key_score(root0) : -INFINITY;
-        float tau = live ? fmaxf(fmaxf(tau_loc, tau_pool), g_seen ? unord32(g_seen) : -INFINITY) : INFINITY;
-        if (live) g_seen = *reinterpret_cast<volatile uint32_t*>(gt);   // lands while this tile is processed
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nst = 0;
         const bool tracing = p.trace != nullptr && blockIdx.x == 0 && warp == 4 && nt < 1000;
@@ -379,10 +399,9 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // Survivors of pass 1 are taken out of the REGISTERS the accumulator chunk was loaded into: every lane
         // that has flagged columns picks ITS OWN lowest one through a select tree, so a round serves up to 32
         // different columns at once and a chunk costs max-over-lanes(#flagged) rounds, not #distinct columns.
-        // A survivor is first parked in a four-entry register stash; the list work happens in ONE place (the drain
-        // at the bottom of the loop: the list code is large, and inlined at several sites it overflowed the
-        // instruction cache), when some lane's stash is full or the tile is done.  Iteration TILE_N/64 of the
-        // chunk loop only drains.
+        // A survivor is first parked in a four-entry register stash and appended in ONE place (the drain at the
+        // bottom of the loop) when some lane's stash is full or the tile is done; iteration TILE_N/64 of the chunk
+        // loop only drains.
 #pragma unroll 1
         for (int ch = 0; ch <= TILE_N / 64; ++ch) {   // 64 accumulator columns at a time
           uint32_t acc0[32], acc1[32];
@@ -418,6 +437,8 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 m1 |= (__uint_as_float(acc1[4 * g + 2]) * n.z >= tau) ? (1u << (4 * g + 2)) : 0u;
                 m1 |= (__uint_as_float(acc1[4 * g + 3]) * n.w >= tau) ? (1u << (4 * g + 3)) : 0u;
               }
+              m0 &= lds_u32_volatile(vstrip + 8 * ch);       // rows outside the corpus / excluded by the row mask
+              m1 &= lds_u32_volatile(vstrip + 8 * ch + 4);
               if (no_insert) m0 = m1 = 0;
             }
           }
@@ -446,47 +467,13 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               for (int i = 0; i < nst; ++i) {
                 const float s = i == 0 ? s0 : (i == 1 ? s1 : (i == 2 ? s2 : s3));
                 const int j = i == 0 ? j0 : (i == 1 ? j1 : (i == 2 ? j2 : j3));
-                const int64_t row = int64_t(t) * TILE_N + j;
-                if (s >= tau && row < p.n_rows && (p.mask == nullptr || p.mask[row] != 0)) {
-                  const uint64_t key = make_key(s, uint32_t(row));
-                  // unlocked pre-check: the root only grows, so a key at or below a stale root is out for good
-                  if (lds_u32_volatile(st_cnt) < uint32_t(p.kk) || key > lds_u64_volatile(st_root)) {
-                    uint64_t root = 0;
-                    bool done = false;
-                    do {   // (the critical section sits INSIDE the retry loop: no lane waits while holding a lock)
-                      if (smem_try_lock(st_lock)) {
-                        const uint32_t cnt = lds_u32_volatile(st_cnt);
-                        root = lds_u64_volatile(st_root);
-                        if (p.debug & 8) {   // timing experiment: no list work at all
-                          root = key;
-                          sts_u64(st_root, root);
-                        } else if (cnt < uint32_t(p.kk)) {
-                          sts_u64(mylist + cnt * LSTRIDE, key);
-                          sts_u32(st_cnt, cnt + 1);
-                          if (cnt + 1 == uint32_t(p.kk)) {
-                            root = heap_build(mylist, p.kk);
-                            sts_u64(st_root, root);
-                          }
-                        } else if (key > root) {
-                          root = heap_replace_root(mylist, p.kk, key);
-                          sts_u64(st_root, root);
-                        }
-                        smem_unlock(st_lock);
-                        done = true;
-                      }
-                    } while (!done);
-                    if (G > 0) {   // running maximum of the row's pool part
-                      const int g = ((j >> 5) * G) >> 3;
-                      const uint32_t o = ord32(s);
-                      if (o > smem_atomic_max_u32(pm_addr + g * 512, o) && !(p.debug & 4))
-                        atomicMax(gs + size_t(g) * p.q_stride, o);
-                    }
-                    if (root) {
-                      tau_loc = key_score(root);
-                      tau = fmaxf(tau, tau_loc);
-                      if (!(p.debug & 4)) atomicMax(gt, ord32(tau_loc));
-                    }
-                  }
+                {
+                  const uint32_t idx = smem_atomic_add_u32(cnt_addr, 1u);
+                  if (idx < uint32_t(p.cap)) mybuf[idx] = make_key(s, uint32_t(t) * TILE_N + uint32_t(j));
+                  // running maximum of the row's pool part
+                  const int g = ((j >> 3) * G) >> 5;
+                  const uint32_t o = ord32(s);
+                  if (o > smem_atomic_max_u32(pm_addr + g * 512, o) && !(p.debug & 4)) atomicMax(gs + size_t(g) * p.q_stride, o);
                 }
               }
               nst = 0;
@@ -500,13 +487,10 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       }
       it += uint32_t(t1 - t0);
-      // ---- hand the list over: both groups are done with it, each writes every other slot
+      // ---- both groups are done with the item: publish how many keys query L's buffer holds
       named_bar_sync(EPI_BAR, 256);
-      if (qb < p.nqb) {   // (the odd block out of a pair carries no queries)
-        uint64_t* dst = p.parts + (size_t(slab) * p.q_stride + size_t(qb) * BLOCK_M + L) * p.kk;
-        for (int c = grp; c < p.kk; c += 2) dst[c] = lds_u64(mylist + c * LSTRIDE);
-      }
-      named_bar_sync(EPI_BAR, 256);   // ... before the next item's list is zeroed
+      if (grp == 0 && live) p.counts[size_t(slab) * p.q_stride + q] = lds_u32_volatile(cnt_addr);
+      named_bar_sync(EPI_BAR, 256);   // ... before the next item's counters are zeroed
     }
   }
 
@@ -573,14 +557,22 @@ static bool cached_map(const void* ptr, int64_t rows, int dim, CUtensorMap& out)
 }
 
 struct Plan {
-  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, pool_g;
+  int nqb, nqb2, n_tiles, n_slabs, n_stages, grid, pool_g, cap;
   size_t smem;
 };
 
-static size_t smem_bytes(int kk, int n_stages, int pool_g) {
-  return 1024 /*align*/ + size_t(n_stages) * STAGE_BYTES + size_t(kk) * BLOCK_M * 8 /*list*/ + BLOCK_M * 16 /*state*/ +
-         size_t(pool_g) * BLOCK_M * 4 /*part maxima*/ + 8 * TILE_N * 4 /*norm strips*/ +
+static size_t smem_bytes(int n_stages, int pool_g) {
+  return 1024 /*align*/ + size_t(n_stages) * STAGE_BYTES + BLOCK_M * 4 /*append counters*/ +
+         size_t(pool_g) * BLOCK_M * 4 /*part maxima*/ + 8 * STRIP_WORDS * 4 /*norm + validity strips*/ +
          (2 * size_t(MAX_STAGES) + 4) * 8 + 64;
+}
+
+// Keys a (slab, query) buffer holds.  A query typically appends a few dozen keys per slab (more while the
+// thresholds warm up, and more for a large k'); a buffer that overflows only costs that query the fast path.
+static int buffer_cap(int kk) {
+  int c = 256;
+  while (c < 4 * kk) c <<= 1;
+  return c;
 }
 
 static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) {
@@ -591,31 +583,30 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   pl.nqb = (n_queries + BLOCK_M - 1) / BLOCK_M;
   pl.nqb2 = (pl.nqb + 1) / 2;
   pl.n_tiles = int((n_rows + TILE_N - 1) / TILE_N);
-  // One item per CTA pair whenever the query blocks fit: every slab of a query block is then resident at the same
-  // time, which the pooled threshold relies on.
+  // One item per CTA pair: every slab of a query block is resident at the same time, which the shared thresholds
+  // rely on.  More query blocks than pairs: not this kernel's shape (the caller splits the batch or falls back).
   const int gp = g / 2;
-  int s = pl.nqb2 <= gp ? gp / pl.nqb2 : 1;
+  if (pl.nqb2 > gp) return false;
+  int s = gp / pl.nqb2;
   if (s > pl.n_tiles) s = pl.n_tiles;
   pl.n_slabs = s < 1 ? 1 : s;
-  const int items = pl.nqb2 * pl.n_slabs;
-  pl.grid = 2 * (items < gp ? items : gp);
-  // pool parts: the smallest G in {1, 2, 4, 8} with (#slabs x G) >= kk; pooling needs every slab of a query block
-  // resident at the same time (one item per pair)
+  pl.grid = 2 * pl.nqb2 * pl.n_slabs;
+  // pool parts: the smallest G in {1, 2, 4, .. 32} with (#slabs x G) >= kk
   pl.pool_g = 0;
-  if (items <= gp)
-    for (int pg = 1; pg <= POOL_GMAX; pg <<= 1)
-      if (pl.n_slabs * pg >= kk) {
-        pl.pool_g = pg;
-        break;
-      }
-  if (smem_bytes(kk, 2, pl.pool_g) > SMEM_LIMIT) return false;
+  for (int pg = 1; pg <= POOL_GMAX; pg <<= 1)
+    if (pl.n_slabs * pg >= kk) {
+      pl.pool_g = pg;
+      break;
+    }
+  if (pl.pool_g == 0) return false;
+  pl.cap = buffer_cap(kk);
   int ns = 2;
-  while (ns < MAX_STAGES && smem_bytes(kk, ns + 1, pl.pool_g) <= SMEM_LIMIT) ++ns;
+  while (ns < MAX_STAGES && smem_bytes(ns + 1, pl.pool_g) <= SMEM_LIMIT) ++ns;
   static const int cap_stages = [] { const char* e = getenv("DRS_PAIR_STAGES"); return e ? atoi(e) : 0; }();   // tuning hook
   if (cap_stages >= 2 && ns > cap_stages) ns = cap_stages;
   pl.n_stages = ns;
-  pl.smem = smem_bytes(kk, ns, pl.pool_g);
-  return true;
+  pl.smem = smem_bytes(ns, pl.pool_g);
+  return pl.smem <= SMEM_LIMIT;
 }
 
 }  // namespace ss2
@@ -626,53 +617,49 @@ bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk) {
   return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) && umma::ss2::encode_tiled() != nullptr;
 }
 
-int dense_pair_parts(int n_queries, int64_t n_rows, int dim, int kk) {
+// Workspace geometry of a call: slabs (= candidate buffers per query), keys per buffer, pool parts (rows of the
+// threshold table) and the u32 words of the zero-initialised area [gslab[pool parts][q_stride] | seed counters].
+bool dense_pair_geometry(int n_queries, int64_t n_rows, int dim, int kk, int q_stride, DensePairGeometry& geo) {
   umma::ss2::Plan pl;
-  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs : 0;
+  if (!umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl)) return false;
+  geo.n_slabs = pl.n_slabs;
+  geo.cap = pl.cap;
+  geo.pool_parts = pl.n_slabs * pl.pool_g;
+  geo.zero_words = size_t(q_stride) * geo.pool_parts + 2 * size_t(pl.nqb2) + 8;
+  geo.query_rows = ((n_queries + 255) / 256) * 256;
+  return true;
 }
-
-// pool parts (rows of the per-part threshold table right after gtau[q_stride]) and the u32 words of the whole
-// zero-initialised threshold area: gtau[q_stride] | gslab[pool parts][q_stride] | seed counters
-int dense_pair_pool_parts(int n_queries, int64_t n_rows, int dim, int kk) {
-  umma::ss2::Plan pl;
-  return umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl) ? pl.n_slabs * pl.pool_g : 0;
-}
-size_t dense_pair_threshold_words(int n_queries, int64_t n_rows, int dim, int kk, int q_stride) {
-  umma::ss2::Plan pl;
-  if (!umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl)) return 0;
-  return size_t(q_stride) * (1 + size_t(pl.n_slabs) * pl.pool_g) + 2 * size_t(pl.nqb2) + 8;
-}
-
-// rows of the bf16 query image the kernel reads through TMA (workspace: rows * dim * 2 bytes, 128-byte aligned)
-int dense_pair_query_rows(int n_queries) { return ((n_queries + 255) / 256) * 256; }
 
 int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
-                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, int q_stride,
-                      uint32_t* d_gtau, void* d_qbf16, cudaStream_t st) {
+                      const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, uint32_t* d_counts,
+                      int q_stride, uint32_t* d_zero_area, void* d_qbf16, cudaStream_t st) {
   using namespace umma;
   using namespace umma::ss2;
   Plan pl;
   DRS_REQUIRE(make_plan(n_queries, n_rows, dim, kk, pl), DRS_ERR_UNSUPPORTED,
-              "dense(tcgen05 pair): needs dim % 64 == 0 and k' small enough for shared memory");
+              "dense(tcgen05 pair): needs dim % 64 == 0 and at most 256 queries per SM pair");
   DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_q) & 15) == 0, DRS_ERR_ARG, "dense: queries not 16-byte aligned");
   DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_qbf16) & 127) == 0, DRS_ERR_ARG, "dense: query image not 128-byte aligned");
-  const int q_rows = dense_pair_query_rows(n_queries);
+  const int q_rows = ((n_queries + 255) / 256) * 256;
   CUtensorMap tmap_q, tmap_c;
   DRS_REQUIRE(cached_map(d_qbf16, q_rows, dim, tmap_q) && cached_map(d_corpus, n_rows, dim, tmap_c), DRS_ERR_CUDA,
               "dense(tcgen05 pair): cuTensorMapEncodeTiled failed or is unavailable");
+  const size_t pool_parts = size_t(pl.n_slabs) * pl.pool_g;
   Params p;
   p.inv_norm = d_inv_norm;
   p.mask = d_mask;
+  p.mask_vec = (reinterpret_cast<uintptr_t>(d_mask) & 7) == 0 ? 1 : 0;
   p.parts = d_parts;
-  p.gtau = d_gtau;
-  p.gslab = d_gtau + q_stride;
-  p.seed_cnt = d_gtau + size_t(q_stride) * (1 + size_t(pl.n_slabs) * pl.pool_g);
+  p.counts = d_counts;
+  p.gslab = d_zero_area;
+  p.seed_cnt = d_zero_area + size_t(q_stride) * pool_parts;
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
   p.nqb2 = pl.nqb2;
   p.dim = dim;
   p.kk = kk;
+  p.cap = pl.cap;
   p.q_stride = q_stride;
   p.n_slabs = pl.n_slabs;
   p.n_tiles = pl.n_tiles;
@@ -692,7 +679,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
     attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
   });
   DRS_CUDA_CHECK(attr_rc);
-  DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, dense_pair_threshold_words(n_queries, n_rows, dim, kk, q_stride) * sizeof(uint32_t), st));
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_zero_area, 0, (size_t(q_stride) * pool_parts + 2 * size_t(pl.nqb2) + 8) * sizeof(uint32_t), st));
   {
     const int64_t n8 = int64_t(q_rows) * dim / 8;
     const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 4 * sm_count()));
@@ -718,8 +705,8 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
     static unsigned long long h[3000];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[pair trace] tiles/slab %d stages %d pool_g %d: tile: wait_done(+cycles since first) busy flagged_cols\n",
-            pl.n_tiles / pl.n_slabs, pl.n_stages, pl.pool_g);
+    fprintf(stderr, "[pair trace] tiles/slab %d stages %d pool_g %d cap %d: tile: wait_done(+cycles since first) busy drains\n",
+            pl.n_tiles / pl.n_slabs, pl.n_stages, pl.pool_g, pl.cap);
     for (int i = 0; i < 1000 && h[3 * i + 1]; ++i)
       fprintf(stderr, "[pair trace] %d %llu %llu %llu\n", i, h[3 * i] - h[0], h[3 * i + 1] - h[3 * i], h[3 * i + 2]);
   }

@@ -144,6 +144,100 @@ __global__ void __launch_bounds__(256) merge_keys_kernel(const uint64_t* __restr
     out[(size_t(blockIdx.y) * out_qstride + q) * kk + i] = buf[i];
 }
 
+// ------------------------------------------------------------------------------------------
+// merge_appended: the CTA-pair tensor kernel APPENDS every row whose approximate score reached the query's shared
+// threshold at the time to one buffer per (slab, query): parts[(slab * q_stride + q) * cap + i], i < counts[..].
+// The final thresholds (min over the pool parts, pool[part * q_stride + q]) are the tightest of all: keys below
+// them are dropped, the kk largest survivors come out descending.  A buffer that overflowed (count > cap: keys
+// were lost) or more survivors than the merge buffer holds set overflow[q]: the query is then treated as
+// unproven and re-run through the exact kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) merge_appended_kernel(const uint64_t* __restrict__ parts,
+                                                             const uint32_t* __restrict__ counts, int n_slabs,
+                                                             int q_stride, int cap, int kk, uint64_t* __restrict__ out,
+                                                             const uint32_t* __restrict__ pool, int n_pool,
+                                                             int32_t* __restrict__ overflow) {
+  __shared__ uint64_t buf[MERGE_BUF];
+  __shared__ unsigned s_off[160];
+  __shared__ unsigned s_bound;
+  __shared__ int s_n, s_ovf;
+  const int q = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_bound = 0xffffffffu;
+    s_n = 0;
+    unsigned acc = 0;
+    int ovf = 0;
+    for (int s = 0; s < n_slabs; ++s) {
+      unsigned c = counts[size_t(s) * q_stride + q];
+      if (c > unsigned(cap)) {
+        ovf = 1;
+        c = unsigned(cap);
+      }
+      s_off[s] = acc;
+      acc += c;
+    }
+    s_off[n_slabs] = acc;
+    s_ovf = ovf;
+  }
+  __syncthreads();
+  {
+    unsigned mn = 0xffffffffu;
+    for (int i = threadIdx.x; i < n_pool; i += blockDim.x) mn = min(mn, pool[size_t(i) * q_stride + q]);
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(&s_bound, mn);
+  }
+  __syncthreads();
+  const unsigned bound = s_bound;   // 0 (some part never reported) keeps everything
+  const unsigned total = s_off[n_slabs];
+  for (unsigned f = threadIdx.x; f < total; f += blockDim.x) {
+    int lo = 0, hi = n_slabs;   // slab of flat index f: last s with s_off[s] <= f
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= f) lo = mid;
+      else hi = mid;
+    }
+    const uint64_t v = parts[(size_t(lo) * q_stride + q) * cap + (f - s_off[lo])];
+    if (unsigned(v >> 32) >= bound) {
+      const int pos = atomicAdd(&s_n, 1);
+      if (pos < MERGE_BUF) buf[pos] = v;
+    }
+  }
+  __syncthreads();
+  int ns = s_n;
+  if (ns > MERGE_BUF) {   // (thresholds that never tightened): keep what fits, mark the query
+    ns = MERGE_BUF;
+    if (threadIdx.x == 0) s_ovf = 1;
+  }
+  uint64_t* dst = out + size_t(q) * kk;
+  if (ns <= 256) {   // rank by counting: keys are distinct
+    const uint64_t key = int(threadIdx.x) < ns ? buf[threadIdx.x] : 0;
+    int rank = 0;
+    if (key != 0)
+      for (int j = 0; j < ns; ++j) rank += buf[j] > key;
+    for (int i = ns + threadIdx.x; i < kk; i += blockDim.x) dst[i] = 0;
+    if (key != 0 && rank < kk) dst[rank] = key;
+  } else {
+    const int m = next_pow2(ns);
+    for (int i = ns + threadIdx.x; i < m; i += blockDim.x) buf[i] = 0;
+    __syncthreads();
+    block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
+    for (int i = threadIdx.x; i < kk; i += blockDim.x) dst[i] = i < m ? buf[i] : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) overflow[q] = s_ovf;
+}
+
+int launch_merge_appended(const uint64_t* d_parts, const uint32_t* d_counts, int n_slabs, int q_stride, int cap,
+                          int n_queries, int kk, uint64_t* d_out, const uint32_t* d_pool, int n_pool,
+                          int32_t* d_overflow, cudaStream_t st) {
+  DRS_REQUIRE(kk > 0 && kk <= MERGE_BUF / 2 && n_slabs > 0 && n_slabs < 160, DRS_ERR_UNSUPPORTED, "merge: sizes out of range");
+  merge_appended_kernel<<<n_queries, 256, 0, st>>>(d_parts, d_counts, n_slabs, q_stride, cap, kk, d_out, d_pool, n_pool,
+                                                   d_overflow);
+  count_launches(1);
+  DRS_CUDA_CHECK(cudaGetLastError());
+  return DRS_OK;
+}
+
 size_t merge_scratch_keys(int n_parts, int n_queries, int kk) {
   if (n_parts <= MERGE_TWO_LEVEL) return 0;
   return size_t((n_parts + MERGE_FANIN - 1) / MERGE_FANIN) * n_queries * kk;
@@ -194,7 +288,7 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
     const float* __restrict__ inv_norm, int dim, const uint64_t* __restrict__ cand, int kk, int kprime,
     float approx_err, float* __restrict__ out_scores, int64_t* __restrict__ out_ids,
     int32_t* __restrict__ flags, const int32_t* __restrict__ active, int query_mode,
-    int flag_value_unproven, int flag_value_proven) {
+    int flag_value_unproven, int flag_value_proven, const int32_t* __restrict__ force_unproven) {
   __shared__ float sq[DRS_MAX_DIM];
   __shared__ uint64_t ekey[RESCORE_MAXC];
   __shared__ double red[8];
@@ -294,6 +388,8 @@ __global__ void __launch_bounds__(256) dense_rescore_kernel(
       const float outside_best = float(double(s_amin) * amin_scale) + err_bound;
       f = (outside_best < tau) ? 0 : flag_value_unproven;
     }
+    // the selection stage lost candidates for this query (a candidate buffer overflowed): nothing is proven
+    if (force_unproven != nullptr && force_unproven[q] != 0) f = flag_value_unproven;
     flags[q] = f;
   }
 }
@@ -302,12 +398,12 @@ int launch_dense_rescore(const float* d_q, int n_queries, const void* d_corpus, 
                          int dim, const uint64_t* d_cand, int kk, int kprime, float approx_err,
                          float* d_out_scores, int64_t* d_out_ids, int32_t* d_flags,
                          const int32_t* d_active, int query_mode, int flag_unproven, int flag_proven,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int32_t* d_force_unproven) {
   DRS_REQUIRE(kk <= RESCORE_MAXC, DRS_ERR_UNSUPPORTED, "rescore: candidate list too long");
   dense_rescore_kernel<<<n_queries, 256, 0, st>>>(d_q, reinterpret_cast<const __nv_bfloat16*>(d_corpus),
                                                    d_inv_norm, dim, d_cand, kk, kprime, approx_err,
                                                    d_out_scores, d_out_ids, d_flags, d_active,
-                                                   query_mode, flag_unproven, flag_proven);
+                                                   query_mode, flag_unproven, flag_proven, d_force_unproven);
   count_launches(1);
   DRS_CUDA_CHECK(cudaGetLastError());
   return DRS_OK;

@@ -223,6 +223,11 @@ __device__ __forceinline__ uint32_t smem_atomic_max_u32(uint32_t addr, uint32_t 
   asm volatile("atom.relaxed.cta.shared.max.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ uint32_t smem_atomic_add_u32(uint32_t addr, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -235,6 +240,9 @@ __device__ __forceinline__ uint64_t lds_u64_volatile(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");

@@ -107,9 +107,10 @@ def test_dense_umma_matches_oracle(n, q, kprime):
     assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
 
 
-# (rows, queries, k', dim): one tile, ragged tiles, odd number of query blocks (an idle half pair), one block
-# (half of every MMA is padding), k' classes with two / one epilogue groups, dims the single-CTA kernel cannot do
-@pytest.mark.parametrize("n,q,kprime,dim", [(64, 1, 4, 768), (255, 129, 10, 768), (4099, 130, 10, 768),
+# (rows, queries, k', dim): few tiles, ragged tiles, odd number of query blocks (an idle half pair), one block
+# (half of every MMA is padding), small and large k' (pool parts of 256 .. 8 columns), dims the single-CTA kernel
+# cannot do
+@pytest.mark.parametrize("n,q,kprime,dim", [(600, 1, 4, 768), (777, 129, 10, 768), (4099, 130, 10, 768),
                                             (50000, 300, 10, 768), (50000, 256, 60, 768), (200000, 1000, 10, 768),
                                             (30000, 257, 100, 768), (70000, 700, 20, 768), (20000, 200, 10, 64),
                                             (20000, 513, 10, 1024), (30000, 384, 30, 320)])
@@ -140,7 +141,8 @@ def test_dense_pair_mask_zero_rows_and_queries():
 
 
 def test_dense_tensor_dispatch():
-    """AUTO / UMMA: the pair kernel from two query blocks on, the single-CTA kernel for one block."""
+    """AUTO / UMMA: the pair kernel from two query blocks on, the single-CTA kernel for one block and for corpora
+    of too few tiles for the pair kernel's shared thresholds (it refuses them when forced)."""
     if not _umma_available():
         pytest.skip("tcgen05 kernel not built")
     emb, qv = _dense_case(20000, 300, seed=17)
@@ -148,6 +150,23 @@ def test_dense_tensor_dispatch():
     assert _lib.load().drs_dense_last_kernel() == 3
     _check_dense(emb, qv[:100].contiguous(), 10, _lib.DENSE_UMMA)
     assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
+    _check_dense(emb[:255].contiguous(), qv, 10, _lib.DENSE_AUTO)
+    assert _lib.load().drs_dense_last_kernel() == _lib.DENSE_UMMA
+    with pytest.raises(NotImplementedError):
+        _check_dense(emb[:255].contiguous(), qv, 10, _lib.DENSE_UMMA_PAIR)
+
+
+def test_dense_pair_buffer_overflow_escalates():
+    """Scores that never let the shared thresholds tighten (all rows identical: every score ties) overflow the
+    candidate buffers; such queries are marked unproven and resolved by the exact kernel."""
+    if not _umma_available():
+        pytest.skip("tcgen05 kernel not built")
+    emb, qv = _dense_case(30000, 260, seed=23)
+    emb[:] = emb[7]              # every row the same vector: every query sees 30000 equal scores
+    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA_PAIR)
+    assert set(np.unique(flags).tolist()) <= {2, 3}
+    ties, flags = _check_dense(emb, qv, 10, _lib.DENSE_UMMA_PAIR, escalate=False)
+    assert (flags == 1).all()
 
 
 def test_dense_umma_without_escalation_flags_are_conservative():
