@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(256) queries_to_bf16_kernel(const float* __res
 constexpr int THREADS = 384;                         // 4 service warps + 2 epilogue groups of 4 warps
 constexpr int POOL_GMAX = 32;                        // pool parts per slab at most (groups of 8 columns of a tile)
 constexpr int EPI_BAR = 1;                           // named barrier of the 8 epilogue warps
+constexpr uint32_t ORD_NEG_INF = 0x007fffffu;        // ord32(-infinity)
 constexpr int STRIP_WORDS = TILE_N + 8;              // per warp: the tile's 256 inverse norms + 256 validity bits
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -265,12 +266,19 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // global kk-th best: a row scoring below it can be dropped for good.
       uint32_t* gs = p.gslab + size_t(slab) * G * p.q_stride + (live ? q : 0);
       float tau = live ? -INFINITY : INFINITY;   // padding lanes never survive
+      // (A part whose rows so far are all invalid -- outside the corpus or masked out -- reports -infinity: it is
+      // left out, and the bound holds as long as kk parts remain.  0 = a part has not reported yet: no bound.)
       auto refresh_pool = [&]() {
         if (live) {
           uint32_t mn = 0xffffffffu;
+          int dead = 0;
           const volatile uint32_t* col = p.gslab + q;
-          for (int sl = 0; sl < n_pool; ++sl) mn = min(mn, col[size_t(sl) * p.q_stride]);
-          if (mn != 0u) tau = fmaxf(tau, unord32(mn));   // 0 = some part has not reported yet
+          for (int sl = 0; sl < n_pool; ++sl) {
+            const uint32_t v = col[size_t(sl) * p.q_stride];
+            if (v == ORD_NEG_INF) ++dead;
+            else mn = min(mn, v);
+          }
+          if (mn != 0u && n_pool - dead >= p.kk) tau = fmaxf(tau, unord32(mn));
         }
       };
       // inverse norms and validity (inside the corpus, passes the row mask) of the tile's 256 rows: lane l fetches
@@ -587,8 +595,10 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   // rely on.  More query blocks than pairs: not this kernel's shape (the caller splits the batch or falls back).
   const int gp = g / 2;
   if (pl.nqb2 > gp) return false;
+  // (at least two tiles per slab: a ragged last tile then shares its pool parts with a full one, and both
+  // epilogue groups of every CTA have work)
   int s = gp / pl.nqb2;
-  if (s > pl.n_tiles) s = pl.n_tiles;
+  if (s > pl.n_tiles / 2) s = pl.n_tiles / 2;
   pl.n_slabs = s < 1 ? 1 : s;
   pl.grid = 2 * pl.nqb2 * pl.n_slabs;
   // pool parts: the smallest G in {1, 2, 4, .. 32} with (#slabs x G) >= kk

@@ -240,7 +240,7 @@ static int launch_one(const float* d_q, int n_queries, int q0, const void* d_cor
 }
 
 // parts must hold dense_simt_grid() * q_stride * kk keys.  With d_active == nullptr every query is
-// served (ceil(Q/QT) passes over the corpus); with d_active set, up to 4 passes of 4 flagged queries.
+// served (ceil(Q/QT) passes over the corpus); with d_active set, one pass per 4 flagged queries.
 int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, const float* d_inv_norm,
                       const uint8_t* d_mask, int64_t n_rows, int dim, int kk, uint64_t* d_parts, int q_stride,
                       const int32_t* d_active, cudaStream_t st) {
@@ -270,7 +270,9 @@ int launch_dense_simt(const float* d_q, int n_queries, const void* d_corpus, con
       q0 += qt;
     }
   } else {
-    const int qt = 4, q0 = 0, pass = 4;   // one launch, up to four passes inside the kernel
+    // one launch; inside the kernel one pass over the corpus per four flagged queries, ending at the first pass
+    // with nothing left to do (normally the first or second)
+    const int qt = 4, q0 = 0, pass = (n_queries + 3) / 4;
     int rc = DRS_ERR_UNSUPPORTED;
     DRS_SIMT_CASE(4, 1) DRS_SIMT_CASE(4, 2) DRS_SIMT_CASE(4, 3) DRS_SIMT_CASE(4, 4)
     if (rc != DRS_OK) return rc;

@@ -160,11 +160,12 @@ __global__ void __launch_bounds__(256) merge_appended_kernel(const uint64_t* __r
   __shared__ uint64_t buf[MERGE_BUF];
   __shared__ unsigned s_off[160];
   __shared__ unsigned s_bound;
-  __shared__ int s_n, s_ovf;
+  __shared__ int s_n, s_ovf, s_dead;
   const int q = blockIdx.x;
   if (threadIdx.x == 0) {
     s_bound = 0xffffffffu;
     s_n = 0;
+    s_dead = 0;
     unsigned acc = 0;
     int ovf = 0;
     for (int s = 0; s < n_slabs; ++s) {
@@ -180,50 +181,66 @@ __global__ void __launch_bounds__(256) merge_appended_kernel(const uint64_t* __r
     s_ovf = ovf;
   }
   __syncthreads();
-  {
+  {   // the kernel's rule: parts without a valid row (-infinity) are left out, kk parts must remain
     unsigned mn = 0xffffffffu;
-    for (int i = threadIdx.x; i < n_pool; i += blockDim.x) mn = min(mn, pool[size_t(i) * q_stride + q]);
+    int dead = 0;
+    for (int i = threadIdx.x; i < n_pool; i += blockDim.x) {
+      const unsigned v = pool[size_t(i) * q_stride + q];
+      if (v == 0x007fffffu) ++dead;
+      else mn = min(mn, v);
+    }
     for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    if ((threadIdx.x & 31) == 0) atomicMin(&s_bound, mn);
+    dead = __reduce_add_sync(0xffffffffu, dead);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_bound, mn);
+      atomicAdd(&s_dead, dead);
+    }
   }
   __syncthreads();
-  const unsigned bound = s_bound;   // 0 (some part never reported) keeps everything
+  const unsigned bound = (n_pool - s_dead >= kk) ? s_bound : 0u;   // 0 (some part never reported) keeps everything
   const unsigned total = s_off[n_slabs];
-  for (unsigned f = threadIdx.x; f < total; f += blockDim.x) {
-    int lo = 0, hi = n_slabs;   // slab of flat index f: last s with s_off[s] <= f
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= f) lo = mid;
-      else hi = mid;
-    }
-    const uint64_t v = parts[(size_t(lo) * q_stride + q) * cap + (f - s_off[lo])];
-    if (unsigned(v >> 32) >= bound) {
-      const int pos = atomicAdd(&s_n, 1);
-      if (pos < MERGE_BUF) buf[pos] = v;
-    }
-  }
-  __syncthreads();
-  int ns = s_n;
-  if (ns > MERGE_BUF) {   // (thresholds that never tightened): keep what fits, mark the query
-    ns = MERGE_BUF;
-    if (threadIdx.x == 0) s_ovf = 1;
-  }
   uint64_t* dst = out + size_t(q) * kk;
-  if (ns <= 256) {   // rank by counting: keys are distinct
-    const uint64_t key = int(threadIdx.x) < ns ? buf[threadIdx.x] : 0;
-    int rank = 0;
-    if (key != 0)
-      for (int j = 0; j < ns; ++j) rank += buf[j] > key;
-    for (int i = ns + threadIdx.x; i < kk; i += blockDim.x) dst[i] = 0;
-    if (key != 0 && rank < kk) dst[rank] = key;
-  } else {
-    const int m = next_pow2(ns);
-    for (int i = ns + threadIdx.x; i < m; i += blockDim.x) buf[i] = 0;
+  // Rounds: the kk best so far sit in buf[0, carry); a round reads at most MERGE_BUF - kk appended keys, keeps the
+  // ones the bound lets through behind them, and sorts.  One round unless the thresholds never tightened.
+  const unsigned batch = unsigned(MERGE_BUF - kk);
+  int carry = 0;
+  for (unsigned base = 0; base == 0 || base < total; base += batch) {
+    const unsigned end = min(total, base + batch);
+    for (unsigned f = base + threadIdx.x; f < end; f += blockDim.x) {
+      int lo = 0, hi = n_slabs;   // slab of flat index f: the last s with s_off[s] <= f
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_off[mid] <= f) lo = mid;
+        else hi = mid;
+      }
+      const uint64_t v = parts[(size_t(lo) * q_stride + q) * cap + (f - s_off[lo])];
+      if (unsigned(v >> 32) >= bound) buf[atomicAdd(&s_n, 1)] = v;
+    }
     __syncthreads();
-    block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
-    for (int i = threadIdx.x; i < kk; i += blockDim.x) dst[i] = i < m ? buf[i] : 0;
+    const int ns = s_n;
+    const bool last = end >= total;
+    if (last && carry == 0 && ns <= 256) {   // the common case: rank by counting (keys are distinct)
+      const uint64_t key = int(threadIdx.x) < ns ? buf[threadIdx.x] : 0;
+      int rank = 0;
+      if (key != 0)
+        for (int j = 0; j < ns; ++j) rank += buf[j] > key;
+      for (int i = ns + threadIdx.x; i < kk; i += blockDim.x) dst[i] = 0;
+      if (key != 0 && rank < kk) dst[rank] = key;
+    } else {
+      const int m = next_pow2(max(ns, 1));
+      for (int i = ns + threadIdx.x; i < m; i += blockDim.x) buf[i] = 0;
+      __syncthreads();
+      block_bitonic_desc(buf, m, [](uint64_t a, uint64_t b) { return a < b; });
+      if (last) {
+        for (int i = threadIdx.x; i < kk; i += blockDim.x) dst[i] = i < ns ? buf[i] : 0;
+      } else {
+        carry = min(ns, kk);
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = carry;
+        __syncthreads();
+      }
+    }
   }
-  __syncthreads();
   if (threadIdx.x == 0) overflow[q] = s_ovf;
 }
 
