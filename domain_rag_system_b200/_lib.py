@@ -49,6 +49,9 @@ EXPORTS = {
     "drs_rerank_cosine": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "drs_merge_candidates_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "drs_merge_candidates_f64": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "drs_candidate_cosines": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "drs_merge_gathered": (C.c_int, [_vp, _i32, _sz, _sz, _i32, _sz, _sz, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "drs_rerank_from_cosines": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -242,3 +245,48 @@ def merge_candidates(scores, ids, k_out):
         _check(fn(_ptr(scores.contiguous()), _ptr(ids.contiguous()), p, q, k, k_out, _ptr(out_s), _ptr(out_i),
                   _stream()))
     return out_s, out_i
+
+
+def candidate_cosines(corpus_bf16, rq_f32, ids, out=None):
+    """cos(rq[q], corpus[ids[q, j]]) in the simple reranker's exact fp32 arithmetic; ids [Q, n] LOCAL rows, -1 -> 0."""
+    _need_cuda(corpus_bf16, rq_f32, ids)
+    q, n = ids.shape
+    out = torch.empty(q, n, dtype=torch.float32, device=ids.device) if out is None else out
+    with torch.cuda.device(ids.device):
+        _check(load().drs_candidate_cosines(_ptr(corpus_bf16), corpus_bf16.shape[1], _ptr(rq_f32), _ptr(ids), q, n,
+                                            _ptr(out), _stream()))
+    return out
+
+
+def merge_gathered(gathered, n_parts, part_stride, off_scores, scores_f64, off_ids, off_cos, id_offset, q, k, k_out,
+                   out=None):
+    """Merge the parts' [Q, k] lists out of a gathered byte buffer -> (scores, ids int64 GLOBAL, cos fp32 or None)."""
+    _need_cuda(gathered, id_offset)
+    dev = gathered.device
+    has_cos = off_cos is not None
+    if out is None:
+        out = (torch.empty(q, k_out, dtype=torch.float64 if scores_f64 else torch.float32, device=dev),
+               torch.empty(q, k_out, dtype=torch.int64, device=dev),
+               torch.empty(q, k_out, dtype=torch.float32, device=dev) if has_cos else None)
+    with torch.cuda.device(dev):
+        _check(load().drs_merge_gathered(_ptr(gathered), n_parts, part_stride, off_scores, 1 if scores_f64 else 0, off_ids,
+                                         off_cos if has_cos else 0, 1 if has_cos else 0, _ptr(id_offset), q, k, k_out,
+                                         _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+    return out
+
+
+def rerank_from_cosines(pool_ids, top_k, v_ids, v_cos, b_ids, b_cos, out=None):
+    """Stable sort of the fused pool by cosines carried in the merged lists -> (scores fp32, ids int64, pos int32)."""
+    ref = pool_ids
+    _need_cuda(ref, v_ids, v_cos, b_ids, b_cos)
+    q, top_n = pool_ids.shape
+    dev = ref.device
+    if out is None:
+        out = (torch.empty(q, top_k, dtype=torch.float32, device=dev), torch.empty(q, top_k, dtype=torch.int64, device=dev),
+               torch.empty(q, top_k, dtype=torch.int32, device=dev))
+    kv = 0 if v_ids is None else v_ids.shape[1]
+    kb = 0 if b_ids is None else b_ids.shape[1]
+    with torch.cuda.device(dev):
+        _check(load().drs_rerank_from_cosines(_ptr(pool_ids), q, top_n, top_k, _ptr(v_ids), _ptr(v_cos), kv, _ptr(b_ids),
+                                              _ptr(b_cos), kb, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _stream()))
+    return out

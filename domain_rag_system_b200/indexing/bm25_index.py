@@ -87,7 +87,8 @@ class Bm25DeviceIndex:
         self = cls()
         build_device = torch.device(build_device or device)
         device = torch.device(device)
-        offs = torch.as_tensor(np.asarray(doc_offsets), dtype=torch.int64)
+        # (numpy arrays / lists, or torch tensors already on a device: nothing is round-tripped through the host)
+        offs = (doc_offsets if torch.is_tensor(doc_offsets) else torch.as_tensor(np.asarray(doc_offsets))).to(torch.int64)
         n = int(offs.numel() - 1)
         if n <= 0:
             raise ValueError("empty corpus")  # rank_bm25 divides by corpus_size
@@ -110,7 +111,7 @@ class Bm25DeviceIndex:
         self.n_docs_global = n_global
         self.avgdl = total_global / n_global
         doc_len = (offs[1:] - offs[:-1]).to(build_device)
-        toks = torch.as_tensor(np.asarray(tokens)).to(build_device, dtype=torch.int64)
+        toks = (tokens if torch.is_tensor(tokens) else torch.as_tensor(np.asarray(tokens))).to(build_device, dtype=torch.int64)
         doc_of_tok = torch.repeat_interleave(torch.arange(n, device=build_device, dtype=torch.int64), doc_len)
         # (term, doc) pairs -> sorted unique with counts == postings with tf
         ukey, tf = torch.unique(toks * n + doc_of_tok, return_counts=True)

@@ -138,3 +138,81 @@ def make_chunks(texts, prefix: str = "chunk"):
     return [{"chunk_id": f"{prefix}_{i}", "doc_id": f"doc_{i // 4}", "source": "synthetic",
              "chunk_type": "body", "text": t, "metadata": {"row": i}}
             for i, t in enumerate(texts)]
+
+
+# --------------------------------------------------------------------------
+# block-seeded corpora: the SAME corpus whatever the number of shards
+# --------------------------------------------------------------------------
+N_BLOCKS = 64
+
+
+def block_bounds(n_total: int, block: int, n_blocks: int = N_BLOCKS):
+    """Rows [lo, hi) of block `block` (contiguous, sizes differ by at most one)."""
+    base, rem = divmod(n_total, n_blocks)
+    lo = block * base + min(block, rem)
+    return lo, lo + base + (1 if block < rem else 0)
+
+
+def shard_blocks(world: int, rank: int, n_blocks: int = N_BLOCKS):
+    """Blocks of rank `rank` when the corpus is row-sharded over `world` ranks (world must divide n_blocks, so that
+    shard boundaries are block boundaries and every rank count sees the identical corpus)."""
+    if n_blocks % world != 0:
+        raise ValueError(f"world size {world} must divide {n_blocks}")
+    per = n_blocks // world
+    return range(rank * per, (rank + 1) * per)
+
+
+def block_embeddings(n_total: int, block: int, dim: int = EMB_DIM, device: str = "cpu") -> torch.Tensor:
+    lo, hi = block_bounds(n_total, block)
+    return unit_embeddings(hi - lo, dim=dim, seed=1234 + block, device=device)
+
+
+def zipf_docs_torch(rows: int, vocab: int = VOCAB, seed: int = 2025, s: float = ZIPF_S, len_min: int = DOC_LEN_MIN,
+                    len_max: int = DOC_LEN_MAX, device: str = "cpu"):
+    """Same distribution as ``zipf_docs`` drawn with torch's generator on `device` (the numpy version takes a minute
+    per 10 M documents): (doc_offsets int64 [rows+1], tokens int32 [total]) as tensors on `device`."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    lens = torch.randint(len_min, len_max + 1, (rows,), generator=g, device=device, dtype=torch.int64)
+    offs = torch.zeros(rows + 1, dtype=torch.int64, device=device)
+    torch.cumsum(lens, 0, out=offs[1:])
+    cdf = torch.from_numpy(_zipf_cdf(vocab, s)).to(device)
+    total = int(offs[-1])
+    toks = torch.empty(total, dtype=torch.int32, device=device)
+    step = 1 << 24
+    for a in range(0, total, step):
+        b = min(total, a + step)
+        u = torch.rand(b - a, generator=g, device=device, dtype=torch.float64)
+        toks[a:b] = torch.searchsorted(cdf, u).clamp_(max=vocab - 1).to(torch.int32)
+    return offs, toks
+
+
+def block_docs(n_total: int, block: int, vocab: int = VOCAB, device: str = "cpu"):
+    lo, hi = block_bounds(n_total, block)
+    return zipf_docs_torch(hi - lo, vocab=vocab, seed=2025 + block, device=device)
+
+
+def shard_corpus(n_total: int, world: int, rank: int, vocab: int = VOCAB, dim: int = EMB_DIM, device: str = "cpu"):
+    """This rank's shard of the block-seeded corpus: (embeddings bf16 [n_local, dim], doc_offsets int64 [n_local+1],
+    tokens int32) on `device`, plus the global row of its first row."""
+    blocks = shard_blocks(world, rank)
+    lo = block_bounds(n_total, blocks[0])[0]
+    hi = block_bounds(n_total, blocks[-1])[1]
+    emb = torch.empty(hi - lo, dim, dtype=torch.bfloat16, device=device)
+    offs_parts, tok_parts, base = [torch.zeros(1, dtype=torch.int64, device=device)], [], 0
+    for b in blocks:
+        a, e = block_bounds(n_total, b)
+        emb[a - lo:e - lo] = block_embeddings(n_total, b, dim=dim, device=device)
+        o, t = block_docs(n_total, b, vocab=vocab, device=device)
+        offs_parts.append(o[1:] + base)
+        tok_parts.append(t)
+        base += int(o[-1])
+    return emb, torch.cat(offs_parts), torch.cat(tok_parts), lo
+
+
+def block_queries(q: int, n_total: int, vocab: int = VOCAB, dim: int = EMB_DIM, device: str = "cpu"):
+    """The query batch of a block-seeded corpus: fp32 unit vectors (seed 4321) and token-id queries whose copied
+    tokens come from documents of block 0 (so every rank can build them without seeing the other shards)."""
+    qv = query_embeddings(q, dim=dim, seed=4321, near_frac=0.0)
+    o, t = block_docs(n_total, 0, vocab=vocab, device=device)
+    qt = zipf_queries(q, o.cpu().numpy(), t.cpu().numpy(), vocab=vocab, seed=777)
+    return qv, qt

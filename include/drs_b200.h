@@ -203,6 +203,33 @@ int drs_merge_candidates_f32(const float* d_scores, const int64_t* d_ids, int n_
 int drs_merge_candidates_f64(const double* d_scores, const int64_t* d_ids, int n_parts, int n_queries,
                              int k, int k_out, double* d_out_scores, int64_t* d_out_ids, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Row-sharded corpora (one process per GPU; no reference counterpart: the reference is single-process).
+ * Each rank fills ONE send buffer with its local lists, an all-gather concatenates the ranks' buffers
+ * ("parts", part_stride_bytes apart), and these entry points work on the gathered buffer in place.
+ *
+ * drs_candidate_cosines: the "simple" reranker's cosine (src/reranker/rerank.py:53-58, the exact fp32
+ *   arithmetic of drs_rerank_cosine) of the rerank query against every LOCAL candidate row of a
+ *   [Q, n] list (-1 -> 0), so that the fused pool can be reranked after the exchange without a second
+ *   one: the cosine travels with the candidate.
+ * drs_merge_gathered: merge of the P parts' [Q, k] lists into [Q, k_out], order (score desc, id desc).
+ *   Scores at off_scores (fp32, or fp64 when scores_f64), int64 LOCAL ids at off_ids, optional fp32
+ *   cosines at off_cos inside each part; d_id_offset[p] = global row of part p's row 0 (NULL: ids are
+ *   global already).  Equals drs_merge_candidates_* on the unpacked lists.
+ * drs_rerank_from_cosines: BaseReranker.rerank's stable sort (src/reranker/rerank.py:29-43) of the fused
+ *   pool [Q, top_n] by cosines looked up in the merged vector / BM25 lists; equals drs_rerank_cosine
+ *   on the unsharded corpus bit for bit.
+ * ------------------------------------------------------------------------------- */
+int drs_candidate_cosines(const void* d_corpus_bf16, int dim, const float* d_rq_f32, const int64_t* d_ids,
+                          int n_queries, int n, float* d_out_cos, void* stream);
+int drs_merge_gathered(const void* d_gathered, int n_parts, size_t part_stride_bytes, size_t off_scores,
+                       int scores_f64, size_t off_ids, size_t off_cos, int has_cos, const int64_t* d_id_offset,
+                       int n_queries, int k, int k_out, void* d_out_scores, int64_t* d_out_ids, float* d_out_cos,
+                       void* stream);
+int drs_rerank_from_cosines(const int64_t* d_pool_ids, int n_queries, int top_n, int top_k, const int64_t* d_v_ids,
+                            const float* d_v_cos, int kv, const int64_t* d_b_ids, const float* d_b_cos, int kb,
+                            float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_pos, void* stream);
+
 /* Which kernel the last drs_dense_topk call on this thread used: DRS_DENSE_SIMT (1), DRS_DENSE_UMMA (2, the
  * single-CTA tensor kernel) or 3 (the CTA-pair tensor kernel). */
 int drs_dense_last_kernel(void);

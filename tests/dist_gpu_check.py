@@ -4,8 +4,9 @@
         tests/dist_gpu_check.py
 
 Every rank builds the SAME small corpus, keeps its row shard, and runs the sharded hybrid search (local
-top-k' -> all-gather of candidate lists over NCCL -> merge -> fusion).  Rank 0 also runs the unsharded path on
-the whole corpus and the CPU oracle; all three must agree (ids exact, RRF scores exact)."""
+top-k' -> all-gather of candidate lists over NCCL -> in-place merge -> fusion -> rerank from the carried cosines),
+eagerly and as a replayed CUDA graph.  Rank 0 also runs the unsharded path on the whole corpus; everything must
+agree bit for bit (ids, fused scores, rerank scores)."""
 import os
 import sys
 
@@ -41,20 +42,29 @@ def main():
     q_terms, q_offs = ix.encode_queries(qt)
     searcher = ShardedHybridSearcher(rows, inv, ix, row_offset=lo)
     ok = True
-    for method in ("rrf", "weighted"):
-        ids, sc = searcher.search_batch(qv.to(dev), q_terms.to(dev), q_offs.to(dev), top_k=top_k, fusion_method=method)
+    qd, qtd, qod = qv.to(dev), q_terms.to(dev), q_offs.to(dev)
+    full = None
+    if rank == 0:
+        full_rows = emb.to(dev)
+        full = ShardedHybridSearcher(full_rows, _lib.row_inv_norms(full_rows),
+                                     Bm25DeviceIndex.from_token_ids(offs, toks, vocab, device=dev, build_device=dev),
+                                     row_offset=0)
+        full.world = 1
+    for method, top_n in (("rrf", 0), ("weighted", 0), ("weighted", 8), ("rrf", 10)):
+        kw = dict(top_k=top_k, fusion_method=method, vector_weight=0.7, bm25_weight=0.3, rerank_top_n=top_n, final_k=5)
+        ids, sc = searcher.search_batch(qd, qtd, qod, **kw)
+        run = searcher.graphed(qd, qtd, qod, **kw)
+        ids_g, sc_g = run()
         torch.cuda.synchronize()
+        graph_ok = bool(torch.equal(ids, ids_g)) and bool(torch.equal(sc, sc_g))
         if rank == 0:
-            full_rows = emb.to(dev)
-            full = ShardedHybridSearcher(full_rows, _lib.row_inv_norms(full_rows),
-                                         Bm25DeviceIndex.from_token_ids(offs, toks, vocab, device=dev, build_device=dev),
-                                         row_offset=0)
-            full.world = 1
-            ids1, sc1 = full.search_batch(qv.to(dev), q_terms.to(dev), q_offs.to(dev), top_k=top_k, fusion_method=method)
+            ids1, sc1 = full.search_batch(qd, qtd, qod, **kw)
             same_ids = bool(torch.equal(ids, ids1))
-            same_sc = bool(torch.equal(sc, sc1)) if method == "rrf" else bool(torch.allclose(sc, sc1, rtol=1e-6))
-            print(f"[dist check] world={world} {method}: ids equal to single-GPU = {same_ids}, scores = {same_sc}")
+            same_sc = bool(torch.equal(sc, sc1))
+            print(f"[dist check] world={world} {method} rerank_top_n={top_n}: ids equal to single-GPU = {same_ids}, "
+                  f"scores bit-equal = {same_sc}, graph replay equal = {graph_ok}")
             ok = ok and same_ids and same_sc
+        ok = ok and graph_ok
     # every rank holds the same answer
     t = torch.tensor([int(ids.sum().item())], device=dev)
     lst = [torch.zeros_like(t) for _ in range(world)]

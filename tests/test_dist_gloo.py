@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from domain_rag_system_b200 import synth
-from domain_rag_system_b200.dist import globalize_ids, pack_candidates, shard_bounds, unpack_candidates
+from domain_rag_system_b200.dist import _Layout, shard_bounds
 from domain_rag_system_b200.indexing.bm25_index import Bm25DeviceIndex
 from oracle import bm25 as obm25
 from oracle import dense as odense
@@ -55,14 +55,23 @@ def _worker(rank, world, port, out):
             v_id[i, :len(r)], v_sc[i, :len(r)] = r, s.astype(np.float32)
             r, s = obm25.bm25_search(orc.get_scores(qt[i]), KP)
             b_id[i, :len(r)], b_sc[i, :len(r)] = r, s
+        # the product's exchange: every rank fills ONE send buffer with its LOCAL lists, one all-gather, and the
+        # gathered buffer is read in place (row offsets of the parts turn local ids into global ones)
         t = torch.from_numpy
-        send = pack_candidates(t(v_sc), globalize_ids(t(v_id), lo), t(b_sc), globalize_ids(t(b_id), lo))
+        lay = _Layout(Q, KP)
+        send = torch.zeros(lay.nbytes, dtype=torch.uint8)
+        v = lay.views(send)
+        v["v_sc"].copy_(t(v_sc)), v["v_ids"].copy_(t(v_id)), v["b_sc"].copy_(t(b_sc)), v["b_ids"].copy_(t(b_id))
         gathered = torch.empty(world * send.numel(), dtype=torch.uint8)
         dist.all_gather_into_tensor(gathered, send)
-        gv_sc, gv_id, gb_sc, gb_id = unpack_candidates(gathered, world, Q, KP, KP)
+        offs_t = torch.zeros(world, dtype=torch.int64)
+        offs_t[rank] = lo
+        dist.all_reduce(offs_t)
+        parts = lay.read_parts(gathered, world)
+        glob = lambda ids: torch.where(ids >= 0, ids + offs_t.view(-1, 1, 1), ids)  # noqa: E731
         if rank == 0:
-            torch.save({"idf": ix.t["idf"], "avgdl": ix.avgdl, "average_idf": ix.average_idf, "gv_sc": gv_sc,
-                        "gv_id": gv_id, "gb_sc": gb_sc, "gb_id": gb_id}, out)
+            torch.save({"idf": ix.t["idf"], "avgdl": ix.avgdl, "average_idf": ix.average_idf, "gv_sc": parts["v_sc"],
+                        "gv_id": glob(parts["v_ids"]), "gb_sc": parts["b_sc"], "gb_id": glob(parts["b_ids"])}, out)
     finally:
         dist.destroy_process_group()
 
@@ -103,15 +112,24 @@ def test_shard_bounds_cover_everything():
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
-def test_pack_unpack_roundtrip():
+def test_send_buffer_layout_roundtrip():
     g = torch.Generator().manual_seed(0)
-    v_sc = torch.rand(3, 4, generator=g)
-    v_id = torch.randint(0, 99, (3, 4), generator=g)
-    b_sc = torch.rand(3, 5, generator=g, dtype=torch.float64)
-    b_id = torch.randint(0, 99, (3, 5), generator=g)
-    buf = pack_candidates(v_sc, v_id, b_sc, b_id)
-    two = torch.cat([buf, buf])
-    a, b, c, d = unpack_candidates(two, 2, 3, 4, 5)
+    q, k = 3, 5
+    lay = _Layout(q, k)
+    assert lay.off_vid % 8 == 0 and lay.off_bid % 8 == 0 and lay.off_bsc % 8 == 0
+    bufs = []
+    vals = []
     for p in range(2):
-        assert torch.equal(a[p], v_sc) and torch.equal(b[p], v_id) and torch.equal(c[p], b_sc) and torch.equal(d[p], b_id)
-    assert globalize_ids(torch.tensor([3, -1]), 10).tolist() == [13, -1]
+        buf = torch.zeros(lay.nbytes, dtype=torch.uint8)
+        v = lay.views(buf)
+        cur = {"v_sc": torch.rand(q, k, generator=g), "v_cos": torch.rand(q, k, generator=g),
+               "b_cos": torch.rand(q, k, generator=g), "v_ids": torch.randint(0, 99, (q, k), generator=g),
+               "b_ids": torch.randint(0, 99, (q, k), generator=g), "b_sc": torch.rand(q, k, generator=g, dtype=torch.float64)}
+        for name, val in cur.items():
+            v[name].copy_(val)
+        bufs.append(buf)
+        vals.append(cur)
+    parts = lay.read_parts(torch.cat(bufs), 2)
+    for p in range(2):
+        for name, val in vals[p].items():
+            assert torch.equal(parts[name][p], val)

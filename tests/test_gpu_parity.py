@@ -578,3 +578,67 @@ def test_vector_indexer_attaches_to_a_qdrant_local_directory(tmp_path):
     assert "vectors" in (tmp_path / "meta.json").read_text()          # qdrant's own metadata is left alone
     vi2 = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
     assert [h["chunk_id"] for h in vi2.search("probe", top_k=3)] == [h["chunk_id"] for h in hits]
+
+
+# ----------------------------------------------------------------------------------------------
+# row-sharded path on ONE GPU: the shards' lists are produced one after the other, laid out exactly as the
+# all-gather would deliver them, and the in-place merge -> fusion -> rerank-from-carried-cosines tail must
+# reproduce the unsharded path bit for bit (what tests/dist_gpu_check.py checks with real ranks over NCCL)
+# ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,method", [(2, "rrf"), (3, "weighted"), (8, "weighted")])
+def test_sharded_tail_emulated_on_one_gpu(world, method):
+    from domain_rag_system_b200.dist import _Layout, shard_bounds
+    n, vocab, nq, top_k, top_n, final_k = 30000, 1500, 70, 15, 30, 5
+    kp = 2 * top_k
+    emb = synth.unit_embeddings(n, seed=77, dup_frac=0.002)
+    offs, toks = synth.zipf_docs(n, vocab=vocab, seed=78)
+    qv = synth.query_embeddings(nq, corpus=emb, seed=79)
+    qt = synth.zipf_queries(nq, offs, toks, vocab=vocab, seed=80)
+    rows = emb.to(DEV)
+    inv = _lib.row_inv_norms(rows)
+    qd = qv.to(DEV).contiguous()
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, vocab, device=DEV)
+    q_terms, q_offs = [t.to(DEV) for t in ix.encode_queries(qt)]
+    # unsharded reference
+    v_sc, v_ids, _ = _lib.dense_topk(qd, rows, inv, kp)
+    b_sc, b_ids = _lib.bm25_topk(ix.struct(), q_terms, q_offs, nq, kp)
+    f_ids, f_sc, _ = _lib.fuse_topk(method, v_sc, v_ids, b_sc, b_ids, top_k, w_vector=0.7, w_bm25=0.3)
+    r_sc, r_ids, r_pos = _lib.rerank_cosine(rows, qd, f_ids[:, :top_n].contiguous(), final_k)
+    # the shards' send buffers
+    lay = _Layout(nq, kp)
+    gathered = torch.zeros(world * lay.nbytes, dtype=torch.uint8, device=DEV)
+    id_off = torch.zeros(world, dtype=torch.int64, device=DEV)
+    for p in range(world):
+        lo, hi = shard_bounds(n, world, p)
+        id_off[p] = lo
+        v = lay.views(gathered[p * lay.nbytes:(p + 1) * lay.nbytes])
+        srows = rows[lo:hi].contiguous()
+        sc, ids, _ = _lib.dense_topk(qd, srows, inv[lo:hi].contiguous(), kp)          # a real local dense list
+        v["v_sc"].copy_(sc), v["v_ids"].copy_(ids)
+        # BM25: this shard's members of the global list, as local ids, padded (a shard's own list would hold more,
+        # but nothing that survives the merge)
+        mine = (b_ids >= lo) & (b_ids < hi)
+        order = torch.argsort((~mine).to(torch.int8), dim=1, stable=True)
+        v["b_ids"].copy_(torch.where(torch.gather(mine, 1, order), torch.gather(b_ids, 1, order) - lo,
+                                     torch.full_like(b_ids, -1)))
+        v["b_sc"].copy_(torch.where(torch.gather(mine, 1, order), torch.gather(b_sc, 1, order),
+                                    torch.full_like(b_sc, float("-inf"))))
+        _lib.candidate_cosines(srows, qd, v["v_ids"], out=v["v_cos"])
+        _lib.candidate_cosines(srows, qd, v["b_ids"], out=v["b_cos"])
+    mv_sc, mv_ids, mv_cos = _lib.merge_gathered(gathered, world, lay.nbytes, lay.off_vsc, False, lay.off_vid,
+                                                lay.off_vcos, id_off, nq, kp, kp)
+    mb_sc, mb_ids, mb_cos = _lib.merge_gathered(gathered, world, lay.nbytes, lay.off_bsc, True, lay.off_bid,
+                                                lay.off_bcos, id_off, nq, kp, kp)
+    assert torch.equal(mv_ids, v_ids) and torch.equal(mv_sc, v_sc)
+    assert torch.equal(mb_ids, b_ids) and torch.equal(mb_sc, b_sc)
+    g_ids, g_sc, _ = _lib.fuse_topk(method, mv_sc, mv_ids, mb_sc, mb_ids, top_k, w_vector=0.7, w_bm25=0.3)
+    assert torch.equal(g_ids, f_ids) and torch.equal(g_sc, f_sc)
+    s_sc, s_ids, s_pos = _lib.rerank_from_cosines(g_ids[:, :top_n].contiguous(), final_k, mv_ids, mv_cos, mb_ids, mb_cos)
+    assert torch.equal(s_ids, r_ids) and torch.equal(s_sc, r_sc) and torch.equal(s_pos, r_pos)
+    # and against the oracle's rerank on a few queries
+    for i in range(0, nq, 17):
+        pool = rows[f_ids[i, :top_n]].float().cpu().numpy()
+        cs = np.array([orerank.cosine_f32_seq(qv[i].numpy(), p) for p in pool], dtype=np.float32)
+        order = np.argsort(-cs.astype(np.float64), kind="stable")[:final_k]
+        assert s_ids[i].cpu().tolist() == f_ids[i, :top_n][order].cpu().tolist()
+        assert np.array_equal(s_sc[i].cpu().numpy(), cs[order])
