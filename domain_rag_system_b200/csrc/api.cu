@@ -70,14 +70,14 @@ void prof_end(int kind, cudaStream_t st) {
 // two or more blocks of 128 queries, the single-CTA kernel with the queries parked in tensor memory (dense_umma.cu)
 // for a single block, 0 = neither.  DRS_TENSOR_KERNEL=ts|pair forces one (A/B measurements).
 enum { TENSOR_NONE = 0, TENSOR_TS = 1, TENSOR_PAIR = 2 };
-static int tensor_variant(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
+static int tensor_variant(int kernel, int n_queries, int64_t n_rows, int dim, int kprime) {
   static const int env_forced = [] {
     const char* e = getenv("DRS_TENSOR_KERNEL");
     if (!e) return 0;
     return !strcmp(e, "ts") ? TENSOR_TS : (!strcmp(e, "pair") ? TENSOR_PAIR : 0);
   }();
-  const bool ts_ok = dense_umma_supported(n_queries, n_rows, dim, kk);
-  const bool pair_ok = dense_pair_supported(n_queries, n_rows, dim, kk);
+  const bool ts_ok = dense_umma_supported(n_queries, n_rows, dim, cand_len_umma(kprime));
+  const bool pair_ok = dense_pair_supported(n_queries, n_rows, dim, cand_len_pair(kprime));
   if (kernel == DRS_DENSE_UMMA_TS) return ts_ok ? TENSOR_TS : TENSOR_NONE;
   if (kernel == DRS_DENSE_UMMA_PAIR) return pair_ok ? TENSOR_PAIR : TENSOR_NONE;
   const int forced = env_forced;
@@ -87,8 +87,8 @@ static int tensor_variant(int kernel, int n_queries, int64_t n_rows, int dim, in
   return ts_ok ? TENSOR_TS : (pair_ok ? TENSOR_PAIR : TENSOR_NONE);
 }
 
-static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim, int kk) {
-  const bool umma_ok = tensor_variant(kernel, n_queries, n_rows, dim, kk) != TENSOR_NONE;
+static int pick_dense_kernel(int kernel, int n_queries, int64_t n_rows, int dim, int kprime) {
+  const bool umma_ok = tensor_variant(kernel, n_queries, n_rows, dim, kprime) != TENSOR_NONE;
   if (kernel == DRS_DENSE_UMMA || kernel == DRS_DENSE_UMMA_TS || kernel == DRS_DENSE_UMMA_PAIR)
     return umma_ok ? DRS_DENSE_UMMA : -1;
   if (kernel == DRS_DENSE_SIMT) return DRS_DENSE_SIMT;
@@ -105,10 +105,11 @@ struct DenseWs {
 
 static DenseWs dense_ws(int n_queries, int64_t n_rows, int dim, int kprime, int kernel) {
   DenseWs w{};
-  const size_t kk = cand_len_umma(kprime);   // the longer of the two candidate lengths sizes every buffer
-  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, int(kk));
+  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, kprime);
   w.simt_parts = dense_simt_grid();
-  w.variant = (which == DRS_DENSE_UMMA) ? tensor_variant(kernel, n_queries, n_rows, dim, int(kk)) : TENSOR_NONE;
+  w.variant = (which == DRS_DENSE_UMMA) ? tensor_variant(kernel, n_queries, n_rows, dim, kprime) : TENSOR_NONE;
+  // the longest candidate list any stage of this call carries sizes every buffer
+  const size_t kk = w.variant == TENSOR_PAIR ? size_t(cand_len_pair(kprime)) : size_t(cand_len_umma(kprime));
   w.umma_qstride = ((n_queries + 127) / 128) * 128;
   w.umma_parts = w.variant == TENSOR_TS ? dense_umma_parts(n_queries, n_rows, dim, int(kk)) : 0;
   size_t umma_keys = size_t(w.umma_parts) * w.umma_qstride * kk, thr_words = size_t(w.umma_qstride) * (1 + size_t(w.umma_parts));
@@ -184,11 +185,12 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   DRS_REQUIRE(n_rows < (int64_t(1) << 32), DRS_ERR_UNSUPPORTED, "dense: more than 2^32-1 rows in one shard");
   DRS_REQUIRE((reinterpret_cast<uintptr_t>(d_corpus_bf16) & 15) == 0, DRS_ERR_ARG, "dense: corpus not 16-byte aligned");
   if (n_queries == 0) return DRS_OK;
-  const int kk_s = cand_len(kprime), kk = cand_len_umma(kprime);
-  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, kk);
+  const int kk_s = cand_len(kprime);
+  const int which = pick_dense_kernel(kernel, n_queries, n_rows, dim, kprime);
   DRS_REQUIRE(which > 0, DRS_ERR_UNSUPPORTED, "dense: tensor-core kernel does not support this shape");
   const DenseWs w = dense_ws(n_queries, n_rows, dim, kprime, kernel);
   DRS_REQUIRE(workspace_bytes >= w.total, DRS_ERR_WORKSPACE, "dense: workspace too small");
+  const int kk = w.variant == TENSOR_PAIR ? cand_len_pair(kprime) : cand_len_umma(kprime);
   cudaStream_t st = (cudaStream_t)stream;
   uint64_t* parts = reinterpret_cast<uint64_t*>(d_workspace);
   uint64_t* cand = parts + w.parts_keys;
@@ -222,8 +224,8 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
     }
     if (rc != DRS_OK) return rc;
     ProfScope pt(DRS_PROF_DENSE_TAIL, st);
-    rc = launch_merge_appended(parts, counts, w.geo.n_slabs, w.umma_qstride, w.geo.cap, n_queries, kk, cand, gtau,
-                               w.geo.pool_parts, ovf, st);
+    rc = launch_merge_appended(parts, counts, w.geo.n_slabs, w.umma_qstride, w.geo.cap, n_queries, kk, cand,
+                               gtau + w.umma_qstride, w.geo.pool_parts, ovf, st);
     if (rc != DRS_OK) return rc;
     rc = launch_dense_rescore(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, dim, cand, kk, kprime, 2e-5f,
                               d_out_scores, d_out_ids, flags, nullptr, dense_umma_query_mode(), 1, 0, st, ovf);
@@ -245,6 +247,7 @@ extern "C" int drs_dense_topk(const float* d_queries_f32, int n_queries, const v
   if (rc != DRS_OK || !escalate) return rc;
   // Re-run the (few) queries whose tensor-core result is not proven exact through the fp32 kernel.
   // Everything is predicated on flags[] on the device; with no flagged query the kernels exit at once.
+  ProfScope pe(DRS_PROF_DENSE_TAIL, st);
   rc = launch_dense_simt(d_queries_f32, n_queries, d_corpus_bf16, d_inv_norm, d_row_mask, n_rows, dim, kk_s, parts,
                          n_queries, flags, st);
   if (rc != DRS_OK) return rc;

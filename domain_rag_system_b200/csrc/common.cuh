@@ -139,6 +139,14 @@ __host__ __device__ __forceinline__ int cand_len(int kprime) { return kprime + 8
 // carries a wider margin: the exactness proof needs the gap between the k'-th exact and the
 // kk-th approximate score to exceed that error, which k'+24 makes near-certain.
 __host__ __device__ __forceinline__ int cand_len_umma(int kprime) { return kprime + 24 + (kprime >> 2); }
+// The CTA-pair kernel keeps no list on chip, so its candidate list can afford a margin that makes the proof fail
+// only on genuine near-ties: the gap between the k'-th and the (2k'+32)-th best score of a corpus is several times
+// the bf16 rounding bound, where k'+24 left ~3 % of the queries of a 10 M-chunk corpus at k' = 60 unproven (each
+// costing a pass of the exact kernel).  Bounded by the re-scoring kernel's list (256).
+__host__ __device__ __forceinline__ int cand_len_pair(int kprime) {
+  const int c = 2 * kprime + 32;
+  return c < 64 ? 64 : (c > 256 ? 256 : c);
+}
 
 // ---- launchers implemented in the .cu files ---------------------------------------------
 // select.cu

@@ -56,8 +56,9 @@ struct Params {
   const uint8_t* mask;
   uint64_t* parts;     // [n_slabs][q_stride][cap] appended keys
   uint32_t* counts;    // [n_slabs][q_stride] keys appended (may exceed cap: the excess was dropped = overflow)
+  uint32_t* gtau;      // [q_stride] zero-initialised: the queries' shared thresholds (ordered-u32, atomicMax)
   uint32_t* gslab;     // [n_slabs * pool_g][q_stride] zero-initialised: running maximum of every pool part
-  uint32_t* seed_cnt;  // [2 * nqb2] zero-initialised: epilogue warps of a query block that are past their seed pass
+  uint32_t* seed_cnt;  // [2][2 * nqb2] zero-initialised: epilogue warps of a query block past the two seed steps
   int64_t n_rows;
   int n_queries, nqb, nqb2, dim, kk, cap, q_stride, n_slabs, n_tiles, n_stages;
   int pool_g;          // pool parts per slab (1, 2, .. 32: groups of 256 / pool_g columns of a tile)
@@ -105,6 +106,8 @@ constexpr int THREADS = 384;                         // 4 service warps + 2 epil
 constexpr int POOL_GMAX = 32;                        // pool parts per slab at most (groups of 8 columns of a tile)
 constexpr int EPI_BAR = 1;                           // named barrier of the 8 epilogue warps
 constexpr uint32_t ORD_NEG_INF = 0x007fffffu;        // ord32(-infinity)
+constexpr int POOL_PER_LANE = 10;                    // pool parts a lane holds in the warp-wide selection
+constexpr int POOL_MAX = 32 * POOL_PER_LANE;         // pool parts per query at most
 constexpr int STRIP_WORDS = TILE_N + 8;              // per warp: the tile's 256 inverse norms + 256 validity bits
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -259,26 +262,43 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
       named_bar_sync(EPI_BAR, 256);
       uint64_t* mybuf = p.parts + (size_t(slab) * p.q_stride + (live ? q : 0)) * p.cap;
-      // Pool parts.  The corpus is cut into n_pool = (#slabs x G) disjoint PARTS: part (v, g) = the rows of slab v
-      // that sit in column group g (256 / G columns) of their tile.  All slabs of a query block run concurrently
-      // and publish the running MAXIMUM of each of their parts in gslab[part][q].  If every part has a row scoring
-      // >= x the corpus has >= n_pool >= kk such rows, so x = min over the parts is a valid lower bound of the
-      // global kk-th best: a row scoring below it can be dropped for good.
+      // Pool parts and the shared threshold.  The corpus is cut into n_pool = (#slabs x G) disjoint PARTS: part (v, g)
+      // = the rows of slab v that sit in column group g (256 / G columns) of their tile.  All slabs of a query block
+      // run concurrently and publish the running MAXIMUM of each of their parts in gslab[part][q].  If kk different
+      // parts each hold a row scoring >= x, the corpus has >= kk such rows: the kk-th LARGEST part maximum is a valid
+      // lower bound of the query's kk-th best score, and with about twice as many parts as kk it is close to it (a
+      // row below it can be dropped for good).  Selecting it costs a few hundred instructions, so it is computed
+      // for every query by ONE warp (the query's owner among the slabs' epilogue warps, all 32 lanes cooperating)
+      // and shared through gtau[q] (atomicMax); everybody else reads gtau[q] once per tile.
       uint32_t* gs = p.gslab + size_t(slab) * G * p.q_stride + (live ? q : 0);
+      const volatile uint32_t* gt = p.gtau + (live ? q : 0);
       float tau = live ? -INFINITY : INFINITY;   // padding lanes never survive
-      // (A part whose rows so far are all invalid -- outside the corpus or masked out -- reports -infinity: it is
-      // left out, and the bound holds as long as kk parts remain.  0 = a part has not reported yet: no bound.)
-      auto refresh_pool = [&]() {
-        if (live) {
-          uint32_t mn = 0xffffffffu;
-          int dead = 0;
-          const volatile uint32_t* col = p.gslab + q;
-          for (int sl = 0; sl < n_pool; ++sl) {
-            const uint32_t v = col[size_t(sl) * p.q_stride];
-            if (v == ORD_NEG_INF) ++dead;
-            else mn = min(mn, v);
+      const bool owner = live && (L % (2 * p.n_slabs)) == 2 * slab + grp;
+      auto publish_bounds = [&]() {
+        uint32_t todo = __ballot_sync(0xffffffffu, owner);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int qq = __shfl_sync(0xffffffffu, q, src);
+          // my share of query qq's part maxima; parts without a valid row so far (-infinity) or that have not
+          // reported (0) count for nothing
+          uint32_t v[POOL_PER_LANE];
+#pragma unroll
+          for (int j = 0; j < POOL_PER_LANE; ++j) {
+            const int part = lane + 32 * j;
+            uint32_t x = part < n_pool ? __ldcg(p.gslab + size_t(part) * p.q_stride + qq) : 0u;
+            v[j] = x == ORD_NEG_INF ? 0u : x;
           }
-          if (mn != 0u && n_pool - dead >= p.kk) tau = fmaxf(tau, unord32(mn));
+          uint32_t cur = 0;   // the largest x with at least kk parts >= x, bit by bit
+#pragma unroll 1
+          for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t x = cur | (1u << bit);
+            int c = 0;
+#pragma unroll
+            for (int j = 0; j < POOL_PER_LANE; ++j) c += v[j] >= x;
+            if (__reduce_add_sync(0xffffffffu, c) >= p.kk) cur = x;
+          }
+          if (lane == src && cur > ORD_NEG_INF) atomicMax(p.gtau + qq, cur);
         }
       };
       // inverse norms and validity (inside the corpus, passes the row mask) of the tile's 256 rows: lane l fetches
@@ -323,9 +343,28 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // Seed rendezvous: every epilogue warp working on this block of 128 queries counts itself in once its first
       // tile's part maxima are published (or at once if it has no tile / cannot seed).
       const uint32_t seed_expect = uint32_t(p.n_slabs * 8);
-      uint32_t* seed_ctr = p.seed_cnt + qb;
+      uint32_t* seed_ctr = p.seed_cnt + qb;                    // step 1: part maxima of the first tiles published
+      uint32_t* seed_ctr2 = p.seed_cnt + 2 * p.nqb2 + qb;      // step 2: the owners' bounds published
       const bool seeding = !(p.debug & 16);
-      if (seeding && t_first >= t1 && lane == 0) atomicAdd(seed_ctr, 1u);
+      auto rendezvous = [&](uint32_t* ctr) {   // count this warp in, wait (bounded) for all the others
+        __threadfence();
+        __syncwarp();
+        int all_in = 0;
+        if (lane == 0) {
+          atomicAdd(ctr, 1u);
+          const long long w0 = clock64();
+          do {
+            all_in = *reinterpret_cast<volatile uint32_t*>(ctr) >= seed_expect ? 1 : 0;
+          } while (!all_in && clock64() - w0 < 60000);
+        }
+        all_in = __shfl_sync(0xffffffffu, all_in, 0);
+        __threadfence();
+        return all_in != 0;
+      };
+      if (seeding && t_first >= t1) {   // a warp without a tile in this item still takes part in both steps
+        if (rendezvous(seed_ctr)) publish_bounds();
+        rendezvous(seed_ctr2);
+      }
       load_norms(t_first);
       int nt = 0, next_refresh = 1;
       for (int t = t_first; t < t1; t += 2, ++nt) {
@@ -338,7 +377,7 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         load_norms(t + 2);                               // prefetch for my next tile
         // the bound moves fastest early on: refreshed before tiles 1, 2, 3, 4, 6, 9, 13, ... then every 32nd
         if (nt == next_refresh) {
-          refresh_pool();
+          publish_bounds();
           next_refresh += min(32, max(1, nt >> 1));
         }
         const uint32_t as = itt & 1u, aph = (itt >> 1) & 1;
@@ -382,21 +421,12 @@ dense_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (live)
               for (int g = 0; g < G; ++g) atomicMax(gs + size_t(g) * p.q_stride, lds_u32_volatile(pm_addr + g * 512));
           }
-          __threadfence();
-          __syncwarp();
-          int all_in = 0;
-          if (lane == 0) {
-            atomicAdd(seed_ctr, 1u);
-            const long long w0 = clock64();
-            do {
-              all_in = *reinterpret_cast<volatile uint32_t*>(seed_ctr) >= seed_expect ? 1 : 0;
-            } while (!all_in && clock64() - w0 < 60000);
-          }
-          all_in = __shfl_sync(0xffffffffu, all_in, 0);
-          if (all_in) {
-            __threadfence();
-            refresh_pool();
-          }
+          if (rendezvous(seed_ctr)) publish_bounds();
+          rendezvous(seed_ctr2);
+        }
+        {   // the query's shared threshold (whoever published it last)
+          const uint32_t g = *gt;
+          if (g != 0u) tau = fmaxf(tau, unord32(g));
         }
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         int j0 = 0, j1 = 0, j2 = 0, j3 = 0, nst = 0;
@@ -601,13 +631,15 @@ static bool make_plan(int n_queries, int64_t n_rows, int dim, int kk, Plan& pl) 
   if (s > pl.n_tiles / 2) s = pl.n_tiles / 2;
   pl.n_slabs = s < 1 ? 1 : s;
   pl.grid = 2 * pl.nqb2 * pl.n_slabs;
-  // pool parts: the smallest G in {1, 2, 4, .. 32} with (#slabs x G) >= kk
+  // pool parts per slab: a power of two G <= 32 with kk <= (#slabs x G) <= POOL_MAX, about 2 kk parts if possible (the
+  // kk-th largest of ~2 kk part maxima tracks the kk-th best score closely; of exactly kk it is their minimum)
   pl.pool_g = 0;
-  for (int pg = 1; pg <= POOL_GMAX; pg <<= 1)
-    if (pl.n_slabs * pg >= kk) {
-      pl.pool_g = pg;
-      break;
-    }
+  for (int pg = 1; pg <= POOL_GMAX; pg <<= 1) {
+    const int parts = pl.n_slabs * pg;
+    if (parts > POOL_MAX) break;
+    if (parts >= kk) pl.pool_g = pg;
+    if (parts >= 2 * kk) break;
+  }
   if (pl.pool_g == 0) return false;
   pl.cap = buffer_cap(kk);
   int ns = 2;
@@ -628,14 +660,15 @@ bool dense_pair_supported(int n_queries, int64_t n_rows, int dim, int kk) {
 }
 
 // Workspace geometry of a call: slabs (= candidate buffers per query), keys per buffer, pool parts (rows of the
-// threshold table) and the u32 words of the zero-initialised area [gslab[pool parts][q_stride] | seed counters].
+// threshold table) and the u32 words of the zero-initialised area [gtau[q_stride] | gslab[pool parts][q_stride] |
+// seed counters].
 bool dense_pair_geometry(int n_queries, int64_t n_rows, int dim, int kk, int q_stride, DensePairGeometry& geo) {
   umma::ss2::Plan pl;
   if (!umma::ss2::make_plan(n_queries, n_rows, dim, kk, pl)) return false;
   geo.n_slabs = pl.n_slabs;
   geo.cap = pl.cap;
   geo.pool_parts = pl.n_slabs * pl.pool_g;
-  geo.zero_words = size_t(q_stride) * geo.pool_parts + 2 * size_t(pl.nqb2) + 8;
+  geo.zero_words = size_t(q_stride) * (1 + geo.pool_parts) + 4 * size_t(pl.nqb2) + 8;
   geo.query_rows = ((n_queries + 255) / 256) * 256;
   return true;
 }
@@ -661,8 +694,9 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   p.mask_vec = (reinterpret_cast<uintptr_t>(d_mask) & 7) == 0 ? 1 : 0;
   p.parts = d_parts;
   p.counts = d_counts;
-  p.gslab = d_zero_area;
-  p.seed_cnt = d_zero_area + size_t(q_stride) * pool_parts;
+  p.gtau = d_zero_area;
+  p.gslab = d_zero_area + q_stride;
+  p.seed_cnt = d_zero_area + size_t(q_stride) * (1 + pool_parts);
   p.n_rows = n_rows;
   p.n_queries = n_queries;
   p.nqb = pl.nqb;
@@ -689,7 +723,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
     attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
   });
   DRS_CUDA_CHECK(attr_rc);
-  DRS_CUDA_CHECK(cudaMemsetAsync(d_zero_area, 0, (size_t(q_stride) * pool_parts + 2 * size_t(pl.nqb2) + 8) * sizeof(uint32_t), st));
+  DRS_CUDA_CHECK(cudaMemsetAsync(d_zero_area, 0, (size_t(q_stride) * (1 + pool_parts) + 4 * size_t(pl.nqb2) + 8) * sizeof(uint32_t), st));
   {
     const int64_t n8 = int64_t(q_rows) * dim / 8;
     const int blocks = int(std::min<int64_t>((n8 + 255) / 256, 4 * sm_count()));

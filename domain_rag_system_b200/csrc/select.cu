@@ -181,23 +181,29 @@ __global__ void __launch_bounds__(256) merge_appended_kernel(const uint64_t* __r
     s_ovf = ovf;
   }
   __syncthreads();
-  {   // the kernel's rule: parts without a valid row (-infinity) are left out, kk parts must remain
-    unsigned mn = 0xffffffffu;
-    int dead = 0;
-    for (int i = threadIdx.x; i < n_pool; i += blockDim.x) {
-      const unsigned v = pool[size_t(i) * q_stride + q];
-      if (v == 0x007fffffu) ++dead;
-      else mn = min(mn, v);
+  {   // the kernel's rule: the kk-th largest maximum among the parts that hold a valid row (-infinity = none, 0 = never
+      // reported) bounds the kk-th best score from below; 0 if fewer than kk such parts exist
+    unsigned cur = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned x = cur | (1u << bit);
+      int c = 0;
+      for (int i = threadIdx.x; i < n_pool; i += blockDim.x) {
+        const unsigned v = pool[size_t(i) * q_stride + q];
+        c += (v != 0x007fffffu) && (v >= x);
+      }
+      // block-wide sum of c
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (threadIdx.x == 0) s_dead = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_dead, c);
+      __syncthreads();
+      if (s_dead >= kk) cur = x;
+      __syncthreads();
     }
-    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    dead = __reduce_add_sync(0xffffffffu, dead);
-    if ((threadIdx.x & 31) == 0) {
-      atomicMin(&s_bound, mn);
-      atomicAdd(&s_dead, dead);
-    }
+    if (threadIdx.x == 0) s_bound = cur > 0x007fffffu ? cur : 0u;
   }
   __syncthreads();
-  const unsigned bound = (n_pool - s_dead >= kk) ? s_bound : 0u;   // 0 (some part never reported) keeps everything
+  const unsigned bound = s_bound;   // 0 keeps everything
   const unsigned total = s_off[n_slabs];
   uint64_t* dst = out + size_t(q) * kk;
   // Rounds: the kk best so far sit in buf[0, carry); a round reads at most MERGE_BUF - kk appended keys, keeps the

@@ -110,7 +110,7 @@ def test_dense_umma_matches_oracle(n, q, kprime):
 # (rows, queries, k', dim): few tiles, ragged tiles, odd number of query blocks (an idle half pair), one block
 # (half of every MMA is padding), small and large k' (pool parts of 256 .. 8 columns), dims the single-CTA kernel
 # cannot do
-@pytest.mark.parametrize("n,q,kprime,dim", [(600, 1, 4, 768), (777, 129, 10, 768), (4099, 130, 10, 768),
+@pytest.mark.parametrize("n,q,kprime,dim", [(3000, 1, 4, 768), (2100, 129, 10, 768), (4099, 130, 10, 768),
                                             (50000, 300, 10, 768), (50000, 256, 60, 768), (200000, 1000, 10, 768),
                                             (30000, 257, 100, 768), (70000, 700, 20, 768), (20000, 200, 10, 64),
                                             (20000, 513, 10, 1024), (30000, 384, 30, 320)])
