@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip config1 / latency / config3")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step only (no CUDA-graph replay)")
     ap.add_argument("--latency-calls", type=int, default=300)
+    ap.add_argument("--config3-chunks", type=int, default=100_000_000, help="size of the 8-GPU extra (test hook)")
     return ap.parse_args()
 
 
@@ -68,6 +69,14 @@ def measured_peaks():
     except Exception:
         return {"tflops_sustained": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0,
                 "source": "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained, 6.65 TB/s)"}
+
+
+_T0 = time.time()
+
+
+def log(msg):
+    """Progress on stderr (stdout carries the one JSON line)."""
+    print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def fetch_k_of(args):
@@ -313,7 +322,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     lib = _lib.load()
     kernel = {"auto": _lib.DENSE_AUTO, "simt": _lib.DENSE_SIMT, "umma": _lib.DENSE_UMMA, "ts": _lib.DENSE_UMMA_TS,
               "pair": _lib.DENSE_UMMA_PAIR}[args.dense_kernel]
@@ -354,6 +364,7 @@ def run_ours(args):
                                         group=True if world > 1 else None)
     torch.cuda.synchronize()
     t_build = time.time() - t_build
+    log(f"shard of {n_local} chunks + BM25 index resident ({t_build:.1f}s)")
     searcher = ShardedHybridSearcher(emb, inv, ix, row_offset=lo)
 
     # ---- queries (identical on every rank: derived from block 0) --------------------------------
@@ -377,6 +388,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_eager()
     torch.cuda.synchronize()
+    log("warm-up done")
 
     # ---- timed region 1: eager launches, every kernel bracketed by CUDA events (roofline, breakdown) ------
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -386,6 +398,7 @@ def run_ours(args):
     prof = _lib.profile_read()
     _lib.profile_enable(False)
     launches = int(lib.drs_kernel_launches() - launches0)
+    log(f"eager region: {ms_eager / args.steps:.3f} ms/step")
 
     # ---- timed region 2: the same step replayed as ONE CUDA graph (local kernels + all-gather + tail) ------
     run, graph_err = None, None
@@ -403,6 +416,7 @@ def run_ours(args):
         ms_graph, win_graph = timed(step_graph, args.steps)
     else:
         step_graph, ms_graph, win_graph = step_eager, ms_eager, win_eager
+    log(f"graph region: {ms_graph / args.steps:.3f} ms/step (error: {graph_err})")
     use_graph = run is not None and ms_graph <= ms_eager
     step_best = step_graph if use_graph else step_eager
     ms_total, win = (ms_graph, win_graph) if use_graph else (ms_eager, win_eager)
@@ -485,16 +499,22 @@ def run_ours(args):
     roofline_bm25["frac"] = roofline_bm25["achieved"] / peaks["hbm_gbs"]
     breakdown = {k: (v[0] / args.steps) for k, v in prof.items()}
 
+    log(f"e2e region: {ms_e2e / args.steps:.3f} ms/step")
     extras = {}
     if not args.no_extras:
         extras = run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, qt, qv_d, kernel, timed,
                             dense_roofline)
 
+    log("extras done")
     if world > 1:
         barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
     if rank != 0:
-        return
+        # (no destroy_process_group: tearing NCCL down while CUDA graphs that captured its kernels are alive can
+        # hang; the process has nothing left to do)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     # ---- parity + CPU baseline (rank 0, on its host cores, at every N) ------------------------------------
     parity, cpu_baseline = None, None
@@ -506,7 +526,9 @@ def run_ours(args):
         del emb, inv, ix, searcher
         torch.cuda.empty_cache()
         corpus = CpuCorpus(args.chunks, args.vocab, [qt[i] for i in idx], device=str(dev))
+        log(f"CPU corpus + oracle index built ({corpus.build_s:.0f}s, {threads} threads)")
         ref = corpus.answers(qv, qt, idx, args)
+        log("oracle answers of the parity sample done")
         hit = sum(len(set(ref[j][0]) & set(ids_gpu[i].tolist())) for j, i in enumerate(idx))
         same_ids = sum(ref[j][0] == ids_gpu[i].tolist() for j, i in enumerate(idx))
         same_sc = sum(ref[j][0] == ids_gpu[i].tolist() and
@@ -545,6 +567,10 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if sampler:
         sampler.stop()
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, qt, qv_d, kernel, timed,
@@ -648,7 +674,7 @@ def run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, q
 
     # ---- configs[3]: 100 M chunks over 8 GPUs (12.5 M rows per GPU), top_k = 10 (k' = 20), RRF --------------------
     if world == 8:
-        n3 = 100_000_000
+        n3 = args.config3_chunks
         e3, o3, t3, lo3 = synth.shard_corpus(n3, world, rank, vocab=args.vocab, device=str(dev))
         i3 = _lib.row_inv_norms(e3)
         ix3 = Bm25DeviceIndex.from_token_ids(o3, t3, args.vocab, device=dev, build_device=dev, group=group)

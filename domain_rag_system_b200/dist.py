@@ -58,11 +58,14 @@ class ShardedHybridSearcher:
     """Batched hybrid search over a row-sharded corpus.  Every rank returns the same result (GLOBAL row ids)."""
 
     def __init__(self, rows_bf16: torch.Tensor, inv_norm: torch.Tensor, bm25_index, row_offset: int,
-                 group=None, fusion_key: Optional[torch.Tensor] = None):
+                 group=None, fusion_key: Optional[torch.Tensor] = None, world: Optional[int] = None):
+        """``world`` = 1 makes a purely local searcher even inside an initialised process group (NO collective is
+        issued, here or later); by default the group's size is used and the constructor is itself a collective (one
+        all-gather of the shards' row offsets), so every rank of the group must construct its searcher."""
         self.rows, self.inv_norm, self.bm25 = rows_bf16, inv_norm, bm25_index
         self.row_offset = int(row_offset)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = int(world) if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.fusion_key = fusion_key            # int64 [N_global] or None
         self._ws_d, self._ws_b = _lib.Workspace(), _lib.Workspace()
         self._bufs = {}

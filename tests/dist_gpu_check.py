@@ -27,7 +27,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
     n, vocab, nq, top_k = 60_000, 3000, 200, 10
     emb = synth.unit_embeddings(n, seed=1234, dup_frac=0.001)
     offs, toks = synth.zipf_docs(n, vocab=vocab, seed=2025)
@@ -48,14 +49,16 @@ def main():
         full_rows = emb.to(dev)
         full = ShardedHybridSearcher(full_rows, _lib.row_inv_norms(full_rows),
                                      Bm25DeviceIndex.from_token_ids(offs, toks, vocab, device=dev, build_device=dev),
-                                     row_offset=0)
-        full.world = 1
+                                     row_offset=0, world=1)
     for method, top_n in (("rrf", 0), ("weighted", 0), ("weighted", 8), ("rrf", 10)):
         kw = dict(top_k=top_k, fusion_method=method, vector_weight=0.7, bm25_weight=0.3, rerank_top_n=top_n, final_k=5)
         ids, sc = searcher.search_batch(qd, qtd, qod, **kw)
+        torch.cuda.synchronize()
+        print(f"[dist check r{rank}] eager step done ({method}, rerank {top_n})", file=sys.stderr, flush=True)
         run = searcher.graphed(qd, qtd, qod, **kw)
         ids_g, sc_g = run()
         torch.cuda.synchronize()
+        print(f"[dist check r{rank}] graph replay done", file=sys.stderr, flush=True)
         graph_ok = bool(torch.equal(ids, ids_g)) and bool(torch.equal(sc, sc_g))
         if rank == 0:
             ids1, sc1 = full.search_batch(qd, qtd, qod, **kw)
@@ -74,9 +77,12 @@ def main():
         print(f"[dist check] all ranks agree: {agree}")
         ok = ok and agree
         print("DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED")
-    dist.destroy_process_group()
-    if rank == 0 and not ok:
-        sys.exit(1)
+    # (no destroy_process_group: tearing NCCL down while CUDA graphs that captured its kernels are alive can hang)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0 if (rank != 0 or ok) else 1)
 
 
 if __name__ == "__main__":
