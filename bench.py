@@ -502,8 +502,11 @@ def run_ours(args):
     log(f"e2e region: {ms_e2e / args.steps:.3f} ms/step")
     extras = {}
     if not args.no_extras:
-        extras = run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, qt, qv_d, kernel, timed,
-                            dense_roofline)
+        try:
+            extras = run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, qt, qv_d, kernel, timed,
+                                dense_roofline, log)
+        except Exception as ex:   # the main line must survive a failing extra
+            extras = {"extras_error": f"{type(ex).__name__}: {ex}"[:300]}
 
     log("extras done")
     if world > 1:
@@ -574,7 +577,7 @@ def run_ours(args):
 
 
 def run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, qt, qv_d, kernel, timed,
-               dense_roofline):
+               dense_roofline, log):
     """The other BASELINE configurations, as extra keys (each timed like the main step: warm-up, then K eager steps
     with CUDA events around every kernel, max over ranks)."""
     import torch.distributed as dist
@@ -618,6 +621,7 @@ def run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, q
     out["config1"]["workload"] = (f"BASELINE configs[1]: {n1 * world} chunks (the first {n1} rows of every shard), "
                                   f"{args.queries}-query batch, top_k=5, RRF, no rerank")
     del ix1, s1
+    log("config1 done")
 
     # ---- configs[4] latency mode: single query against the whole index, rerank_top_n = 50 (k' = 100) --------------
     if world == 1 and args.latency_calls > 0:
@@ -677,7 +681,9 @@ def run_extras(args, world, rank, dev, emb, inv, offs, toks, ix, searcher, qv, q
         n3 = args.config3_chunks
         e3, o3, t3, lo3 = synth.shard_corpus(n3, world, rank, vocab=args.vocab, device=str(dev))
         i3 = _lib.row_inv_norms(e3)
+        log(f"config3: shard of {e3.shape[0]} chunks generated")
         ix3 = Bm25DeviceIndex.from_token_ids(o3, t3, args.vocab, device=dev, build_device=dev, group=group)
+        log("config3: BM25 index built")
         del o3, t3
         torch.cuda.empty_cache()
         s3 = ShardedHybridSearcher(e3, i3, ix3, row_offset=lo3)

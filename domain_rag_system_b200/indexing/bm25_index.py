@@ -137,27 +137,26 @@ class Bm25DeviceIndex:
             dist.all_reduce(df_stat, group=grp)
         df_h = df_stat.cpu().numpy()
         n_local, n = n, n_global          # idf uses the GLOBAL corpus size
+        # idf[t] = math.log(N - df + 0.5) - math.log(df + 0.5): Python's math.log (not bit-equal to a vectorised log),
+        # evaluated once per DISTINCT df (a few thousand values, not V); the running sum that becomes average_idf
+        # follows dict-insertion order = order of first appearance (math.fsum would differ: plain left-to-right adds)
         order = np.argsort(first_pos.cpu().numpy(), kind="stable")
-        idf = np.zeros(self.n_terms, dtype=np.float64)
-        idf_sum = 0
-        neg = []
-        present = 0
-        for t in order:
-            d = int(df_h[t])
-            if d == 0:
-                continue
-            v = math.log(n - d + 0.5) - math.log(d + 0.5)
-            idf[t] = v
-            idf_sum += v
-            present += 1
-            if v < 0:
-                neg.append(t)
-        if present == 0:
+        order = order[df_h[order] > 0]
+        if order.size == 0:
             raise ValueError("corpus has no tokens")  # rank_bm25: division by zero in average_idf
-        self.vocab_present = present
-        self.average_idf = idf_sum / present
-        if neg:
-            idf[np.array(neg, dtype=np.int64)] = self.epsilon * self.average_idf
+        udf, inv = np.unique(df_h[order], return_inverse=True)
+        uval = np.array([math.log(n - int(d) + 0.5) - math.log(int(d) + 0.5) for d in udf], dtype=np.float64)
+        vals = uval[inv]
+        idf = np.zeros(self.n_terms, dtype=np.float64)
+        idf[order] = vals
+        idf_sum = 0
+        for v in vals.tolist():          # sequential fp64 adds in insertion order, as rank_bm25 does
+            idf_sum += v
+        self.vocab_present = int(order.size)
+        self.average_idf = idf_sum / self.vocab_present
+        neg = order[vals < 0]
+        if neg.size:
+            idf[neg] = self.epsilon * self.average_idf
         n = n_local
         # per-document length normaliser, fp64, reference operation order
         dl_h = doc_len.cpu().numpy()
@@ -241,19 +240,14 @@ class Bm25DeviceIndex:
     def from_token_lists(cls, tokenized_corpus: Sequence[Sequence[str]], k1=1.5, b=0.75, epsilon=0.25,
                          device="cuda", tile_docs=None, build_device=None):
         """The drop-in path: documents are lists of token strings."""
-        vocab: Dict[str, int] = {}
         lens = np.fromiter((len(d) for d in tokenized_corpus), dtype=np.int64, count=len(tokenized_corpus))
         offs = np.zeros(len(tokenized_corpus) + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
-        toks = np.empty(int(offs[-1]), dtype=np.int32)
-        p = 0
-        for doc in tokenized_corpus:
-            for w in doc:
-                i = vocab.get(w)
-                if i is None:
-                    i = vocab[w] = len(vocab)
-                toks[p] = i
-                p += 1
+        # term ids in order of first appearance (= rank_bm25's dict insertion order), without a Python loop per
+        # token: one flat pass builds the vocabulary (dict.setdefault runs in C under map), one fromiter the ids
+        vocab: Dict[str, int] = {}
+        flat = [w for doc in tokenized_corpus for w in doc]
+        toks = np.fromiter(map(lambda w: vocab.setdefault(w, len(vocab)), flat), dtype=np.int32, count=len(flat))
         self = cls.from_token_ids(offs, toks, max(len(vocab), 1), k1, b, epsilon, device, tile_docs, build_device)
         self.vocab = vocab
         return self
@@ -307,6 +301,36 @@ class Bm25DeviceIndex:
         if pinned:
             qt, qo = qt.pin_memory(), qo.pin_memory()
         return qt, qo
+
+    # -- wide windows ---------------------------------------------------------------------------
+    def exact_scores(self, term_ids) -> torch.Tensor:
+        """fp64 BM25 score of EVERY local document for one query (term ids of its token occurrences, -1 = OOV), on
+        the device with rank_bm25's arithmetic and operation order (``score += idf * (tf * (k1 + 1) / (tf + kd))``
+        per occurrence, in query order; ``BM25Okapi.get_scores``): bit-identical to the CUDA kernel's re-scored
+        values.  O(sum of df) torch work per query: the path for result windows wider than DRS_MAX_KPRIME."""
+        t = self.t
+        dev = t["post_doc"].device
+        score = torch.zeros(self.n_docs, dtype=torch.float64, device=dev)
+        to = t["term_offsets"]
+        for term in term_ids:
+            term = int(term)
+            if term < 0 or term >= self.n_terms:
+                continue
+            a, e = int(to[term]), int(to[term + 1])
+            if e == a:
+                continue
+            docs = t["post_doc"][a:e].long()
+            tf = (t["post_tf"][a:e].to(torch.int32) & 0xFFFF).to(torch.float64)
+            contrib = t["idf"][term] * (tf * (self.k1 + 1) / (tf + t["doc_kd"][docs]))
+            score.index_add_(0, docs, contrib)       # at most one posting per (term, document): no collisions
+        return score
+
+    def wide_topk(self, term_ids, k: int):
+        """(scores fp64 [k], ids int64 [k]) of one query in the reference's order (score descending, larger row first
+        among ties), for any k <= n_docs."""
+        sc = self.exact_scores(term_ids)
+        order = torch.flip(torch.argsort(sc, stable=True), dims=[0])[:k]     # == np.argsort(kind='stable')[::-1][:k]
+        return sc[order], order
 
     def df_of(self, term_ids) -> np.ndarray:
         to = self.t["term_offsets"]

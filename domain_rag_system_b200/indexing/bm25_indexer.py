@@ -109,8 +109,14 @@ class BM25Indexer:
         qt, qo = self.bm25.encode_queries([self.tokenize(query)])
         fetch = top_k * 2 if filters else top_k        # the reference takes argsort[::-1][:top_k*2] (:128)
         fetch = max(1, min(fetch, self.bm25.n_docs))
-        scores, ids = self.topk_terms(qt.to(self.device), qo.to(self.device), 1, fetch)
-        scores, ids = scores[0].cpu().numpy(), ids[0].cpu().numpy()
+        if fetch <= _lib.MAX_KPRIME:
+            scores, ids = self.topk_terms(qt.to(self.device), qo.to(self.device), 1, fetch)
+            scores, ids = scores[0].cpu().numpy(), ids[0].cpu().numpy()
+        else:
+            # a window wider than the selection kernel's lists (e.g. top_k = 100 with filters => 200): exact fp64
+            # scores of every document on the device, same arithmetic, then the reference's argsort order
+            scores, ids = self.bm25.wide_topk(qt.tolist(), fetch)
+            scores, ids = scores.cpu().numpy(), ids.cpu().numpy()
         results = []
         for idx, s in zip(ids, scores):
             if idx < 0:

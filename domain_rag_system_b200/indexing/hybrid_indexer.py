@@ -181,6 +181,85 @@ class HybridIndexer:
             out.update(rerank_scores=r_sc, rerank_ids=r_ids, rerank_pos=r_pos)
         return out
 
+    def search_many(self, queries: Sequence[str], top_k: int = 10, vector_weight: float = 0.5,
+                    bm25_weight: float = 0.5, fusion_method: str = "rrf", rerank_top_n: int = 0,
+                    rerank_queries: Optional[Sequence[str]] = None, final_k: Optional[int] = None) -> List[List[Dict]]:
+        """The batched caller (the evaluation loop of evaluation/comprehensive_evaluation.py:298-328 in one call):
+        for every query the list ``search(query, top_k, ...)`` would return -- and, with ``rerank_top_n`` > 0, what
+        ``build_reranker('simple', top_n=rerank_top_n).rerank(rerank_query, that_list, top_k=final_k)`` makes of it
+        -- with ONE embedding call, one query encoding and one pass of the CUDA path for the whole batch.
+        ``rerank_queries``: the raw queries the reranker embeds (scripts/query.py:160); default: ``queries``."""
+        if not queries:
+            return []
+        vi, bi = self.vector_indexer, self.bm25_indexer
+        dev = self._device()
+        qv = None
+        if vi is not None:
+            qv = torch.from_numpy(np.ascontiguousarray(np.asarray(vi.embedder.encode(list(queries)), dtype=np.float32))).to(dev)
+        if bi is not None:
+            qt, qo = bi.bm25.encode_queries([bi.tokenize(q) for q in queries])
+            qt, qo = qt.to(dev), qo.to(dev)
+        else:
+            qt = qo = None
+        nq = len(queries)
+        kprime = top_k * 2
+        v_sc = v_ids = b_sc = b_ids = None
+        if vi is not None and vi.rows is not None and vi.rows.shape[0]:
+            v_sc, v_ids, _ = vi.topk_vectors(qv, min(kprime, vi.rows.shape[0]))
+        if bi is not None:
+            b_sc, b_ids = bi.topk_terms(qt, qo, nq, min(kprime, bi.bm25.n_docs))
+        if v_ids is None and b_ids is None:
+            return [[] for _ in queries]
+        ids, scores, norm = _lib.fuse_topk(fusion_method, v_sc, v_ids, b_sc, b_ids, top_k, fusion_key=self.fusion_keys(),
+                                           w_vector=vector_weight, w_bm25=bm25_weight, want_norm=True)
+        r_ids = r_sc = r_pos = None
+        if rerank_top_n and vi is not None:
+            rq = qv
+            if rerank_queries is not None:
+                rq = torch.from_numpy(np.ascontiguousarray(np.asarray(vi.embedder.encode(list(rerank_queries)),
+                                                                      dtype=np.float32))).to(dev)
+            pool = ids[:, : min(rerank_top_n, ids.shape[1])].contiguous()
+            r_sc, r_ids, r_pos = _lib.rerank_cosine(vi.rows, rq, pool, min(final_k or top_k, pool.shape[1]))
+            r_sc, r_pos = r_sc.cpu().numpy(), r_pos.cpu().numpy()
+        ids_h, sc_h, nm_h = ids.cpu().numpy(), scores.cpu().numpy(), norm.cpu().numpy()
+        out = []
+        for i in range(nq):
+            fused = []
+            for row, s, nm in zip(ids_h[i], sc_h[i], nm_h[i]):
+                if row < 0:
+                    break
+                r = self._payload_dict(int(row))
+                if not math.isnan(nm):
+                    r["normalized_score"] = float(nm)       # the key the weighted mode leaks (:184)
+                r["score"] = float(s)
+                r["fusion_method"] = fusion_method if fusion_method == "rrf" else "weighted"
+                fused.append(r)
+            if r_pos is None:
+                out.append(fused)
+                continue
+            rer = []
+            for s, pos in zip(r_sc[i], r_pos[i]):
+                if pos < 0:
+                    break
+                r = fused[int(pos)].copy()
+                r["rerank_score"] = float(s)
+                r["fusion_method"] = (r.get("fusion_method") or "pre") + "+rerank"
+                rer.append(r)
+            out.append(rer)
+        return out
+
+    def _payload_dict(self, row: int) -> Dict:
+        """The result dict of a row, as VectorIndexer.search / BM25Indexer.search build it (without a score)."""
+        vi = self.vector_indexer
+        if vi is not None and vi.payloads:
+            p = vi.payloads[row]
+            return {"chunk_id": p["chunk_id"], "doc_id": p["doc_id"], "source": p["source"],
+                    "chunk_type": p["chunk_type"], "text": p["text"], "metadata": p["metadata"]}
+        from .bm25_indexer import format_result
+        r = format_result(self.bm25_indexer.chunks[row], row, 0.0)
+        r.pop("score", None)
+        return r
+
     # -- hybrid_indexer.py:220-246 ----------------------------------------------------------------
     def save_bm25(self, filepath: str = None):
         if filepath is None:

@@ -54,13 +54,18 @@ class _Shim:
             self.__dict__.update(inner if isinstance(inner, dict) else state)
 
 
+_NUMPY_OK = {("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"),
+             ("numpy._core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+             ("numpy._core.multiarray", "scalar")}
+
+
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] in _SHIM_ROOTS:
             return type(name, (_Shim,), {"__module__": module})
         if (module, name) in _SAFE:
             return super().find_class(module, name)
-        if module.split(".")[0] == "numpy":            # vectors may have been stored as arrays
+        if (module, name) in _NUMPY_OK:                # vectors may have been stored as arrays: only what rebuilds one
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a Qdrant point blob")
 

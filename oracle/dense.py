@@ -56,6 +56,13 @@ def dot_scores(rows: np.ndarray, query) -> np.ndarray:
     return np.ascontiguousarray(rows, dtype=np.float32).astype(np.float64) @ q
 
 
+def euclid_scores(rows: np.ndarray, query) -> np.ndarray:
+    """``Distance.EUCLID`` (``vector_indexer.py:57-62``): nothing is normalised, score = ||query - row||_2 of the
+    stored fp32 rows against the fp64 query; SMALLER is better (``dense_search(..., smaller_is_better=True)``)."""
+    q = np.array(list(np.asarray(query).tolist()), dtype=np.float64)
+    return np.linalg.norm(q[None, :] - np.ascontiguousarray(rows, dtype=np.float32).astype(np.float64), axis=1)
+
+
 def cosine_scores_batch(rows_normed: np.ndarray, queries: np.ndarray, block: int = 1 << 15) -> np.ndarray:
     """fp64 [Q, N] scores for a batch (BLAS dgemm per block)."""
     q = np.asarray(queries, dtype=np.float64)
@@ -68,11 +75,12 @@ def cosine_scores_batch(rows_normed: np.ndarray, queries: np.ndarray, block: int
     return out
 
 
-def dense_search(scores: np.ndarray, limit: int, row_passes=None, score_threshold=None):
+def dense_search(scores: np.ndarray, limit: int, row_passes=None, score_threshold=None, smaller_is_better=False):
     """Walk of the sorted order (local-mode ``search``): filter BEFORE counting,
-    threshold break.  Tie rule: larger row first (``argsort(kind='stable')[::-1]``).
+    threshold break.  Tie rule: larger row first (``argsort(kind='stable')[::-1]``); for distances
+    (``smaller_is_better``) the order is ascending and the threshold cuts what lies ABOVE it.
     Returns (rows int64, scores float64 holding Python-float values)."""
-    order = np.argsort(scores, kind="stable")[::-1]
+    order = np.argsort(-scores if smaller_is_better else scores, kind="stable")[::-1]
     rows, out = [], []
     for idx in order:
         if len(rows) >= limit:
@@ -80,7 +88,7 @@ def dense_search(scores: np.ndarray, limit: int, row_passes=None, score_threshol
         if row_passes is not None and not row_passes(int(idx)):
             continue
         s = float(scores[idx])
-        if score_threshold is not None and s < score_threshold:
+        if score_threshold is not None and (s > score_threshold if smaller_is_better else s < score_threshold):
             break
         rows.append(int(idx))
         out.append(s)

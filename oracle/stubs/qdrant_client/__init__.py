@@ -26,14 +26,21 @@ class QdrantClient:
         self._c.pop(collection_name, None)
 
     def upsert(self, collection_name, points, **_):
+        """Insert, or OVERWRITE the point that already carries the id (that is what an upsert is)."""
         c = self._c[collection_name]
+        pos = {pid: i for i, pid in enumerate(c["ids"])}
         for p in points:
             v = np.asarray(p.vector, dtype=np.float32)[None, :]
             if c["cfg"].distance == models.Distance.COSINE:
                 v = _dense.normalize_rows(v)
-            c["ids"].append(p.id)
-            c["vecs"].append(v[0])
-            c["payload"].append(p.payload)
+            if p.id in pos:
+                i = pos[p.id]
+                c["vecs"][i], c["payload"][i] = v[0], p.payload
+            else:
+                pos[p.id] = len(c["ids"])
+                c["ids"].append(p.id)
+                c["vecs"].append(v[0])
+                c["payload"].append(p.payload)
         c["mat"] = None
 
     def get_collection(self, collection_name):
@@ -45,9 +52,13 @@ class QdrantClient:
         if c["mat"] is None:
             c["mat"] = (np.stack(c["vecs"]) if c["vecs"]
                         else np.zeros((0, c["cfg"].size), dtype=np.float32))
-        if c["cfg"].distance != models.Distance.COSINE:
-            raise NotImplementedError("stand-in covers Distance.COSINE only")
-        scores = _dense.cosine_scores(c["mat"], query, exact_rows=True)
+        smaller = False
+        if c["cfg"].distance == models.Distance.COSINE:
+            scores = _dense.cosine_scores(c["mat"], query, exact_rows=True)
+        elif c["cfg"].distance == models.Distance.DOT:
+            scores = _dense.dot_scores(c["mat"], query)
+        else:
+            scores, smaller = _dense.euclid_scores(c["mat"], query), True
         passes = None
         if query_filter is not None and query_filter.must:
             conds = query_filter.must
@@ -55,7 +66,7 @@ class QdrantClient:
             def passes(i):
                 pl = c["payload"][i]
                 return all(pl.get(fc.key) == fc.match.value for fc in conds)
-        rows, sc = _dense.dense_search(scores, limit, passes, score_threshold)
+        rows, sc = _dense.dense_search(scores, limit, passes, score_threshold, smaller_is_better=smaller)
         pts = [SimpleNamespace(id=c["ids"][r], score=float(s),
                                payload=c["payload"][r] if with_payload else None)
                for r, s in zip(rows, sc)]

@@ -18,7 +18,8 @@ RAW_KEYS = [
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
-    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "lts__t_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum",
 ]
 
 
@@ -91,7 +92,7 @@ def launch_list(path):
 if __name__ == "__main__":
     rep = sys.argv[1]
     raw_summary(rep)
-    for rx in ("dense_umma", "bm25_select"):
+    for rx in ("dense_pair", "dense_umma", "bm25_select"):
         stall_summary(rep, rx)
     if len(sys.argv) > 2:
         launch_list(sys.argv[2])

@@ -14,9 +14,9 @@ def load_golden(name):
         return json.load(f)
 
 
-def golden_module():
+def golden_module(name="make_golden"):
     import importlib.util
-    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(GOLDEN, name + ".py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m

@@ -313,3 +313,23 @@ def test_qdrant_reader_refuses_foreign_classes(tmp_path):
     con.close()
     with pytest.raises(pickle.UnpicklingError):
         read_qdrant_local(tmp_path, "c")
+
+
+def test_built_objects_contain_blackwell_native_instructions():
+    """The Blackwell-native claim, regression-proof: the built tensor kernels must contain tcgen05 MMAs
+    (UTC*MMA in SASS, the pair kernel in its .2CTA form), TMA tensor loads (UTMALDG) and tensor-memory loads
+    (LDTM) -- and no legacy HMMA tensor path.  Runs where nvcc's cuobjdump is (no GPU needed)."""
+    import shutil
+    import subprocess
+    from domain_rag_system_b200 import build as _build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    _build.build()
+    want = {"dense_pair.o": ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM", "UTCBAR.2CTA.MULTICAST"),
+            "dense_umma.o": ("UTCHMMA", "UTMALDG.2D", "LDTM", "STTM")}
+    for obj, needles in want.items():
+        sass = subprocess.run([cuobjdump, "-sass", os.path.join(_build.CSRC, obj)], capture_output=True, text=True).stdout
+        for n in needles:
+            assert n in sass, f"{obj}: no {n} in SASS"
+        assert " HMMA" not in sass and "HGMMA" not in sass, f"{obj}: legacy tensor-core path present"

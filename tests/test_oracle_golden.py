@@ -163,3 +163,38 @@ def test_bm25_wrapper_overfetch_filter_and_zero_scores():
     # post-filter applies inside the top_k*2 window only (bm25_indexer.py:128,140-147)
     rows, _ = obm25.bm25_search(scores, top_k=2, row_passes=lambda i: i in (0, 4))
     assert rows.tolist() == [4]                    # row 0 lies outside the 4-wide window
+
+
+def test_oracle_filters_thresholds_and_metrics_match_reference_golden():
+    """oracle.dense / oracle.bm25 with payload filters, score thresholds and the dot / euclidean metrics reproduce
+    what the reference's own classes returned (tests/golden/filters_golden.json)."""
+    from helpers import golden_module, load_golden
+    from oracle import dense as odense
+    mod = golden_module("make_filters_golden")
+    g = load_golden("filters_golden.json")
+    emb, offs, toks, qv, qt = mod.inputs(g["params"])
+    from domain_rag_system_b200 import synth
+    chunks = mod.chunks_of(synth.docs_as_text(offs, toks))
+    bm = obm25.Bm25Csr(offs, toks, g["params"]["vocab"])
+    normed = odense.normalize_rows(emb)
+    for c in g["cases"]:
+        qi = c["q"]
+        cos = odense.cosine_scores(normed, qv[qi], exact_rows=True)
+        if c["f"] is None:
+            r, s = odense.dense_search(cos, 40, None, c["threshold"])
+            assert [x[1] for x in c["vector_thr"]] == r.tolist() and [x[2] for x in c["vector_thr"]] == s.tolist()
+            continue
+        flt = g["filters"][c["f"]]
+        passes = lambda i: all(chunks[i].get(k) == v for k, v in flt.items())  # noqa: E731
+        r, s = odense.dense_search(cos, 10, passes)
+        assert [x[1] for x in c["vector"]] == r.tolist() and [x[2] for x in c["vector"]] == s.tolist()
+        r, s = obm25.bm25_search(bm.get_scores(qt[qi]), 10, passes)
+        assert same_up_to_ties([[None, a, b] for a, b in zip(r.tolist(), s.tolist())], [x[:3] for x in c["bm25"]])
+    for qi, want in enumerate(g["metrics"]["euclidean"]):
+        r, s = odense.dense_search(odense.euclid_scores(emb, qv[qi]), 10, smaller_is_better=True)
+        assert [x[1] for x in want["top"]] == r.tolist() and [x[2] for x in want["top"]] == s.tolist()
+        r, s = odense.dense_search(odense.euclid_scores(emb, qv[qi]), 10, None, want["thr"], smaller_is_better=True)
+        assert [x[1] for x in want["top_thr"]] == r.tolist()
+    for qi, want in enumerate(g["metrics"]["dot"]):
+        r, s = odense.dense_search(odense.dot_scores(emb, qv[qi]), 10)
+        assert [x[1] for x in want["top"]] == r.tolist() and [x[2] for x in want["top"]] == s.tolist()
