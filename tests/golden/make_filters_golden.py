@@ -82,7 +82,8 @@ def main():
                     entry["hybrid_top50"] = pack(hi.search(qtext, top_k=50, filters=flt))
                     entry["bm25_top100"] = pack(bi.search(qtext, top_k=100, filters=flt))
                 out["cases"].append(entry)
-            thr = float(vi.search(qtext, top_k=12)[-1]["score"])      # the 12th best score: cuts a top-40 request short
+            top13 = vi.search(qtext, top_k=13)                        # between the 12th and the 13th best score:
+            thr = 0.5 * (top13[11]["score"] + top13[12]["score"])     # cuts a top-40 request short after 12 hits
             out["cases"].append(dict(q=qi, f=None, threshold=thr,
                                      vector_thr=pack(vi.search(qtext, top_k=40, score_threshold=thr)),
                                      vector_thr_filtered=pack(vi.search(qtext, top_k=40, filters=FILTERS[0],
@@ -103,7 +104,7 @@ def main():
             res = []
             for qtext in qtexts:
                 full = vm.search(qtext, top_k=10)
-                thr = full[5]["score"]
+                thr = 0.5 * (full[5]["score"] + full[6]["score"])
                 res.append(dict(top=pack(full), thr=thr, top_thr=pack(vm.search(qtext, top_k=10, score_threshold=thr)),
                                 filtered=pack(vm.search(qtext, top_k=10, filters=FILTERS[1]))))
             out["metrics"][metric] = res

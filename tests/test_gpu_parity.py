@@ -468,8 +468,19 @@ def test_dropin_dot_metric_matches_oracle():
             want, _ = odense.dense_search(full, 10)
             assert np.array_equal(ids[i], want), f"dot q{i}: ids differ"
             assert np.allclose(sc[i], full[want], rtol=1e-3, atol=1e-5)     # north-star tolerance for scores
-    with pytest.raises(NotImplementedError):
-        VectorIndexer(embedder=emb, use_in_memory=True, distance_metric="euclidean", device=DEV)
+    # distance_metric='euclidean' on the same rows: distances, ascending
+    ve = VectorIndexer(embedder=emb, use_in_memory=True, distance_metric="euclidean", device=DEV)
+    ve.create_collection()
+    ve.set_rows(torch.from_numpy(rows))
+    for kernel in (_lib.DENSE_SIMT, _lib.DENSE_UMMA):
+        sc, ids, flags = ve.topk_vectors(torch.from_numpy(q).to(DEV), 10, kernel=kernel)
+        sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+        for i in range(q.shape[0]):
+            full = odense.euclid_scores(stored, q[i])
+            want, _ = odense.dense_search(full, 10, smaller_is_better=True)
+            assert np.array_equal(ids[i], want), f"euclidean q{i}: ids differ"
+            assert np.allclose(sc[i], full[want], rtol=1e-3)
+            assert (np.diff(sc[i]) >= 0).all()
 
 
 def test_dropin_error_behaviour(tmp_path):
