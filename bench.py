@@ -421,8 +421,12 @@ def run_ours(args):
     step_best = step_graph if use_graph else step_eager
     ms_total, win = (ms_graph, win_graph) if use_graph else (ms_eager, win_eager)
 
-    # ---- end to end: pinned host queries -> H2D -> step -> D2H of ids / scores, all inside the timed region ---
+    # ---- end to end: host queries (vectors + token ids) -> term encoding -> pinned buffers -> H2D -> step -> D2H of
+    # ids / scores, all inside the timed region
     def step_e2e():
+        qt_new, qo_new = ix.encode_queries(qt)          # the host-side work of a call: token ids -> term ids
+        q_terms_h.copy_(qt_new)
+        q_offs_h.copy_(qo_new)
         qv_d.copy_(qv_h, non_blocking=True)
         q_terms_d.copy_(q_terms_h, non_blocking=True)
         q_offs_d.copy_(q_offs_h, non_blocking=True)

@@ -739,8 +739,8 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   int* next_query = reinterpret_cast<int*>(gtau + n_queries);   // [2]: one counter per pass
   DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8 + 2 * 4, st));
   const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
-  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  DRS_CUDA_CHECK(cudaFuncSetAttribute(bm25_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  DRS_ENSURE_SMEM((bm25_select_kernel<false>), smem);
+  DRS_ENSURE_SMEM((bm25_select_kernel<true>), smem);
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
     bm25_select_kernel<false><<<gy, BM25_THREADS, smem, st>>>(

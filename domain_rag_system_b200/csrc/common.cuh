@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstring>
 #include <string>
 
@@ -21,6 +22,20 @@ int fail(int code, const std::string& msg);
     cudaError_t _e = (expr);                                                              \
     if (_e != cudaSuccess)                                                                \
       return ::drs::fail(DRS_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+// Raise a kernel's dynamic shared-memory limit only when it grows: the attribute is per device and sticky, so the
+// per-call cost (a driver call per launch in latency mode) is paid once per (call site, device, size).
+#define DRS_ENSURE_SMEM(kern, bytes)                                                                  \
+  do {                                                                                                \
+    static std::atomic<int> drs_hw_[64];                                                              \
+    int drs_dev_ = 0;                                                                                 \
+    DRS_CUDA_CHECK(cudaGetDevice(&drs_dev_));                                                         \
+    const int drs_b_ = int(bytes) + 1;                                                                \
+    if (drs_b_ > drs_hw_[drs_dev_ & 63].load(std::memory_order_relaxed)) {                            \
+      DRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, drs_b_ - 1)); \
+      drs_hw_[drs_dev_ & 63].store(drs_b_, std::memory_order_relaxed);                                \
+    }                                                                                                 \
   } while (0)
 
 #define DRS_REQUIRE(cond, code, msg) \

@@ -717,12 +717,7 @@ int launch_dense_pair(const float* d_q, int n_queries, const void* d_corpus, con
   if (want_trace && !d_trace) cudaMalloc(&d_trace, 3000 * sizeof(unsigned long long));
   p.trace = want_trace ? d_trace : nullptr;
   if (want_trace) cudaMemsetAsync(d_trace, 0, 3000 * sizeof(unsigned long long), st);
-  static std::once_flag attr_once;
-  static cudaError_t attr_rc = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_rc = cudaFuncSetAttribute(dense_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT));
-  });
-  DRS_CUDA_CHECK(attr_rc);
+  DRS_ENSURE_SMEM(dense_pair_kernel, SMEM_LIMIT);
   DRS_CUDA_CHECK(cudaMemsetAsync(d_zero_area, 0, (size_t(q_stride) * (1 + pool_parts) + 4 * size_t(pl.nqb2) + 8) * sizeof(uint32_t), st));
   {
     const int64_t n8 = int64_t(q_rows) * dim / 8;

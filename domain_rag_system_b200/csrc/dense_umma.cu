@@ -623,12 +623,12 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
   p.n_slabs = pl.n_slabs;
   p.n_tiles = pl.n_tiles;
   p.n_stages = pl.n_stages;
-  const char* dbg = getenv("DRS_UMMA_DEBUG");
-  p.debug = dbg ? uint32_t(atoi(dbg)) : 0u;
+  static const uint32_t dbg = [] { const char* e = getenv("DRS_UMMA_DEBUG"); return e ? uint32_t(atoi(e)) : 0u; }();
+  p.debug = dbg;
   DRS_CUDA_CHECK(cudaMemsetAsync(d_gtau, 0, size_t(q_stride) * (1 + pl.n_groups * pl.n_slabs) * sizeof(uint32_t), st));
   if (pl.pair) {
     auto kern = dense_umma_kernel<4, true, false>;
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    DRS_ENSURE_SMEM((kern), pl.smem);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(THREADS);
@@ -643,13 +643,13 @@ int launch_dense_umma(const float* d_q, int n_queries, const void* d_corpus, con
     cfg.numAttrs = 1;
     DRS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmap, p));
   } else if (pl.nbox == 4 && p.n_issuers > 1) {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    DRS_ENSURE_SMEM((dense_umma_kernel<4, false, true>), pl.smem);
     dense_umma_kernel<4, false, true><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   } else if (pl.nbox == 4) {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    DRS_ENSURE_SMEM((dense_umma_kernel<4, false, false>), pl.smem);
     dense_umma_kernel<4, false, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   } else {
-    DRS_CUDA_CHECK(cudaFuncSetAttribute(dense_umma_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    DRS_ENSURE_SMEM((dense_umma_kernel<2, false, false>), pl.smem);
     dense_umma_kernel<2, false, false><<<pl.grid, THREADS, pl.smem, st>>>(tmap, p);
   }
   count_launches(1);

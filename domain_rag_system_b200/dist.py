@@ -69,6 +69,7 @@ class ShardedHybridSearcher:
         self.fusion_key = fusion_key            # int64 [N_global] or None
         self._ws_d, self._ws_b = _lib.Workspace(), _lib.Workspace()
         self._bufs = {}
+        self._side = None
         self._id_offset = None
         if self.world > 1:
             dev = rows_bf16.device
@@ -99,6 +100,16 @@ class ShardedHybridSearcher:
         flags = self._buffers(nq, kprime)["flags"]
         kv = min(kprime, self.rows.shape[0])
         kb = min(kprime, self.bm25.n_docs)
+        # Latency mode (a handful of queries): the dense side is one HBM-bound streaming pass that leaves most issue
+        # slots idle, so BM25 runs beside it on a second stream.  (Not for batches: the tensor kernel needs every SM.)
+        side = None
+        if nq <= 8 and kb == kprime:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                _lib.bm25_topk(self.bm25.struct(), q_terms, q_offsets, nq, kprime, ws=self._ws_b, out=(v["b_sc"], v["b_ids"]))
         if kv == kprime:
             _lib.dense_topk(qvecs, self.rows, self.inv_norm, kprime, kernel=dense_kernel, ws=self._ws_d,
                             out=(v["v_sc"], v["v_ids"], flags))
@@ -107,7 +118,9 @@ class ShardedHybridSearcher:
             v["v_sc"].fill_(float("-inf"))
             v["v_ids"].fill_(-1)
             v["v_sc"][:, :kv], v["v_ids"][:, :kv] = sc, ids
-        if kb == kprime:
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        elif kb == kprime:
             _lib.bm25_topk(self.bm25.struct(), q_terms, q_offsets, nq, kprime, ws=self._ws_b, out=(v["b_sc"], v["b_ids"]))
         else:
             sc, ids = _lib.bm25_topk(self.bm25.struct(), q_terms, q_offsets, nq, kb, ws=self._ws_b)

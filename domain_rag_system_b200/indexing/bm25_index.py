@@ -287,16 +287,24 @@ class Bm25DeviceIndex:
         """Token strings (or term ids) -> (q_terms int32, q_offsets int32) HOST tensors.
         Unknown strings become -1 (``idf.get(q) or 0`` in rank_bm25 => no contribution)."""
         offs = np.zeros(len(queries) + 1, dtype=np.int32)
-        flat: List[int] = []
-        for i, q in enumerate(queries):
-            for w in q:
-                if isinstance(w, str):
-                    flat.append(self.vocab.get(w, -1) if self.vocab is not None else -1)
-                else:
-                    w = int(w)
-                    flat.append(w if 0 <= w < self.n_terms else -1)
-            offs[i + 1] = len(flat)
-        qt = torch.from_numpy(np.asarray(flat, dtype=np.int32).reshape(-1))
+        if len(queries) and all(isinstance(q, np.ndarray) and q.dtype.kind in "iu" for q in queries):
+            # term-id queries (benchmarks, pre-encoded callers): no Python loop per token
+            np.cumsum([len(q) for q in queries], out=offs[1:])
+            ids = np.concatenate(queries).astype(np.int64) if offs[-1] else np.zeros(0, dtype=np.int64)
+            flat_a = np.where((ids >= 0) & (ids < self.n_terms), ids, -1).astype(np.int32)
+        else:
+            flat: List[int] = []
+            get = self.vocab.get if self.vocab is not None else (lambda w, d: d)
+            for i, q in enumerate(queries):
+                for w in q:
+                    if isinstance(w, str):
+                        flat.append(get(w, -1))
+                    else:
+                        w = int(w)
+                        flat.append(w if 0 <= w < self.n_terms else -1)
+                offs[i + 1] = len(flat)
+            flat_a = np.asarray(flat, dtype=np.int32).reshape(-1)
+        qt = torch.from_numpy(flat_a)
         qo = torch.from_numpy(offs)
         if pinned:
             qt, qo = qt.pin_memory(), qo.pin_memory()
