@@ -78,6 +78,69 @@ __host__ __device__ __forceinline__ int bm25_query_shift(int nt) {
   return sh;
 }
 
+// shared-memory integer atomics by 32-bit shared address (one IMAD for the address, no generic-pointer arithmetic)
+__device__ __forceinline__ int smem_atom_add_s32(uint32_t addr, int v) {
+  int r;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(r) : "r"(addr), "r"(v) : "memory");
+  return r;
+}
+__device__ __forceinline__ void smem_red_add_s32(uint32_t addr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// Pass A of bm25_select_kernel on its fast path (tile_docs % 4096 == 0, rows not finer than the score unit):
+// NG head-term rows are summed as packed 16-bit lanes and added to the score tile, two 16-byte groups (16
+// documents) per thread and iteration, all 2*NG loads issued before the first use.  ACC = the tile already holds
+// this query's sums (second and later sweeps); CROSS = note the documents a sweep takes across the threshold.
+// Specialised so that the loop carries no per-row predicates: ~36 instructions per group of 8 documents.
+template <int NG, bool ACC, bool CROSS, class NoteFn>
+__device__ __forceinline__ void bm25_dense_sweep(int4* __restrict__ dst, const int T8, const uint16_t* const* rowp,
+                                                 const int64_t doc0, const int mul, const int tau_s0, const int tid,
+                                                 NoteFn&& note) {
+  const uint4* r[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) r[k] = reinterpret_cast<const uint4*>(rowp[k] + doc0);
+  auto finish = [&](const uint4 w, const int i) {
+    int4 lo4 = make_int4(0, 0, 0, 0), hi4 = lo4;
+    if (ACC) {
+      lo4 = dst[i];
+      hi4 = dst[T8 + i];
+    }
+    lo4.x += int(w.x & 0xffffu) * mul; lo4.y += int(w.x >> 16) * mul;
+    lo4.z += int(w.y & 0xffffu) * mul; lo4.w += int(w.y >> 16) * mul;
+    hi4.x += int(w.z & 0xffffu) * mul; hi4.y += int(w.z >> 16) * mul;
+    hi4.z += int(w.w & 0xffffu) * mul; hi4.w += int(w.w >> 16) * mul;
+    dst[i] = lo4;
+    dst[T8 + i] = hi4;
+    if (CROSS) {
+      if (max(max(max(lo4.x, lo4.y), max(lo4.z, lo4.w)), max(max(hi4.x, hi4.y), max(hi4.z, hi4.w))) >= tau_s0) {
+        const int nv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cv = int((u & 1) ? (ws[u >> 1] >> 16) : (ws[u >> 1] & 0xffffu)) * mul;   // this sweep's share
+          if (nv[u] >= tau_s0 && nv[u] - cv < tau_s0) note((u < 4 ? 0 : 4 * T8) + 4 * i + (u & 3));
+        }
+      }
+    }
+  };
+  for (int i = tid; i < T8; i += 2 * BM25_THREADS) {
+    uint4 a[NG], b[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      a[k] = __ldg(r[k] + i);
+      b[k] = __ldg(r[k] + i + BM25_THREADS);
+    }
+#pragma unroll
+    for (int k = 1; k < NG; ++k) {
+      a[0].x += a[k].x; a[0].y += a[k].y; a[0].z += a[k].z; a[0].w += a[k].w;
+      b[0].x += b[k].x; b[0].y += b[k].y; b[0].z += b[k].z; b[0].w += b[k].w;
+    }
+    finish(a[0], i);
+    finish(b[0], i + BM25_THREADS);
+  }
+}
+
 // EXACT = false: the pre-selection pass (integer scores, top-kk keys per (slice, query)).
 // EXACT = true : the escalation pass for the queries whose pre-selection could not be proven (flags[q] == 1):
 //   same accumulation, but EVERY document whose integer score reaches fx_low[q] -- the smallest integer score
@@ -287,7 +350,32 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
               if (nv[u] >= tau_s0 && nv[u] - cv[u] < tau_s0) note((u < 4 ? 0 : T / 2) + 4 * i + (u & 3));
           }
         };
-        for (int g0 = 0; g0 < nd; g0 += 4) {
+        // Fast path: full-size tiles and rows at least as coarse as the score unit (every benchmark shape).  The
+        // multiplier is hidden from the compiler so that scale + accumulate stays one IMAD per document.
+        const bool fast_a = (T8 % (2 * BM25_THREADS)) == 0 && dk >= 0;
+        int mul = 1 << (dk >= 0 ? dk : 0);
+        asm volatile("" : "+r"(mul));
+        for (int g0 = 0; fast_a && g0 < nd; g0 += 4) {
+          const int ng = min(4, nd - g0);
+          const uint16_t* const* rp = s_rowp + g0;
+#define DRS_SWEEP(NG_)                                                                                 \
+  do {                                                                                                 \
+    if (cross) {                                                                                       \
+      if (tile_init) bm25_dense_sweep<NG_, true, true>(dst, T8, rp, doc0, mul, tau_s0, tid, note);     \
+      else bm25_dense_sweep<NG_, false, true>(dst, T8, rp, doc0, mul, tau_s0, tid, note);              \
+    } else {                                                                                           \
+      if (tile_init) bm25_dense_sweep<NG_, true, false>(dst, T8, rp, doc0, mul, tau_s0, tid, note);    \
+      else bm25_dense_sweep<NG_, false, false>(dst, T8, rp, doc0, mul, tau_s0, tid, note);             \
+    }                                                                                                  \
+  } while (0)
+          if (ng == 4) DRS_SWEEP(4);
+          else if (ng == 3) DRS_SWEEP(3);
+          else if (ng == 2) DRS_SWEEP(2);
+          else DRS_SWEEP(1);
+#undef DRS_SWEEP
+          tile_init = true;   // the same thread owns the same documents in every sweep: no barrier between sweeps
+        }
+        for (int g0 = 0; !fast_a && g0 < nd; g0 += 4) {   // general path: small tiles, rows finer than the unit
           const int ng = min(4, nd - g0);
           const uint4* r0 = reinterpret_cast<const uint4*>(s_rowp[g0] + doc0);
           const uint4* r1 = ng > 1 ? reinterpret_cast<const uint4*>(s_rowp[g0 + 1] + doc0) : r0;
@@ -355,44 +443,84 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           }
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           const int cstart = incl - nch;
-          // software pipeline: the loads of chunk c + 8 are in flight while chunk c is added
-          uint4 d = make_uint4(0, 0, 0, 0);
-          int4 im = make_int4(0, 0, 0, 0);
-          int off = 0, slo = 0, slen = 0;   // my four postings are [off, off + 4) of the term's [slo, slen)
+          // Software pipeline over two register sets (A, B): the loads of chunk c + 8 are in flight while chunk c
+          // is added, and the sets swap roles by unrolling instead of by moving registers.
+          // lo (2 bits), len4 (<= tile + 3: 14 bits) and the owner's first chunk (<= 32 * 65: 12 bits) travel in one shuffle
+          const unsigned pk_mine = unsigned(lo) | (unsigned(len4) << 2) | (unsigned(cstart) << 16);
           auto fetch = [&](int c, uint4& fd, int4& fi, int& foff, int& flo, int& flen) {
             const unsigned m = __ballot_sync(0xffffffffu, c >= cstart && c < incl);   // exactly one lane owns chunk c
             const int src = __ffs(m) - 1;
             const long long sa4 = __shfl_sync(0xffffffffu, a4, src);
-            flo = __shfl_sync(0xffffffffu, lo, src);
-            flen = __shfl_sync(0xffffffffu, len4, src);
-            foff = ((c - __shfl_sync(0xffffffffu, cstart, src)) << 7) + (lane << 2);
+            const unsigned pk = __shfl_sync(0xffffffffu, pk_mine, src);
+            flo = int(pk & 3u);
+            flen = int((pk >> 2) & 0x3fffu);
+            foff = ((c - int(pk >> 16)) << 7) + (lane << 2);
             if (foff < flen) {
               fd = __ldg(reinterpret_cast<const uint4*>(ix.d_post_doc + sa4 + foff));
               fi = __ldg(reinterpret_cast<const int4*>(ix.d_post_impact + sa4 + foff));
             }
           };
-          if (warp < total) fetch(warp, d, im, off, slo, slen);
-          for (int c = warp; c < total; c += BM25_THREADS / 32) {
-            uint4 nd4 = make_uint4(0, 0, 0, 0);
-            int4 ni = make_int4(0, 0, 0, 0);
-            int noff = 0, nlo = 0, nlen = 0;
-            if (c + BM25_THREADS / 32 < total) fetch(c + BM25_THREADS / 32, nd4, ni, noff, nlo, nlen);
-            if (off < slen) {
+          // shared address of score[doc - d0u] = sc_rel + 4 * doc (mod 2^32)
+          // (kept opaque: recomputing it from the CTA's shared window and the tile number costs more than a register)
+          uint32_t sc_rel = uint32_t(__cvta_generic_to_shared(sc)) - 4u * d0u;
+          asm volatile("" : "+r"(sc_rel));
+          const int taum1 = tau_s0 - 1;
+          auto add_chunk = [&](const uint4 d, int4 im, const int off, const int slo, const int slen) {
+            if (off >= slen) return;
+            im.x >>= sh; im.y >>= sh; im.z >>= sh; im.w >>= sh;
+            if (off >= slo && off + 3 < slen) {   // all four postings are the term's: no per-posting predicates
+              if (cross) {
+                // before < tau <= before + v  <=>  0 <= tau - 1 - before < v   (v >= 0 in crossing mode)
+                const int b0 = smem_atom_add_s32(sc_rel + 4u * d.x, im.x), b1 = smem_atom_add_s32(sc_rel + 4u * d.y, im.y);
+                const int b2 = smem_atom_add_s32(sc_rel + 4u * d.z, im.z), b3 = smem_atom_add_s32(sc_rel + 4u * d.w, im.w);
+                const bool c0 = unsigned(taum1 - b0) < unsigned(im.x), c1 = unsigned(taum1 - b1) < unsigned(im.y);
+                const bool c2 = unsigned(taum1 - b2) < unsigned(im.z), c3 = unsigned(taum1 - b3) < unsigned(im.w);
+                if (c0 | c1 | c2 | c3) {
+                  if (c0) note(int(d.x - d0u));
+                  if (c1) note(int(d.y - d0u));
+                  if (c2) note(int(d.z - d0u));
+                  if (c3) note(int(d.w - d0u));
+                }
+              } else {
+                smem_red_add_s32(sc_rel + 4u * d.x, im.x);
+                smem_red_add_s32(sc_rel + 4u * d.y, im.y);
+                smem_red_add_s32(sc_rel + 4u * d.z, im.z);
+                smem_red_add_s32(sc_rel + 4u * d.w, im.w);
+              }
+            } else {   // a term's first or last group
               auto add1 = [&](uint32_t doc, int v) {
-                const int dl = int(doc - d0u);
                 if (cross) {
-                  const int before = atomicAdd(sc + dl, v);
-                  if (before < tau_s0 && before + v >= tau_s0) note(dl);
+                  const int before = smem_atom_add_s32(sc_rel + 4u * doc, v);
+                  if (unsigned(taum1 - before) < unsigned(v)) note(int(doc - d0u));
                 } else {
-                  atomicAdd(sc + dl, v);
+                  smem_red_add_s32(sc_rel + 4u * doc, v);
                 }
               };
-              if (off >= slo) add1(d.x, im.x >> sh);
-              if (off + 1 >= slo && off + 1 < slen) add1(d.y, im.y >> sh);
-              if (off + 2 >= slo && off + 2 < slen) add1(d.z, im.z >> sh);
-              if (off + 3 >= slo && off + 3 < slen) add1(d.w, im.w >> sh);
+              if (off >= slo) add1(d.x, im.x);
+              if (off + 1 >= slo && off + 1 < slen) add1(d.y, im.y);
+              if (off + 2 >= slo && off + 2 < slen) add1(d.z, im.z);
+              if (off + 3 >= slo && off + 3 < slen) add1(d.w, im.w);
             }
-            d = nd4; im = ni; off = noff; slo = nlo; slen = nlen;
+          };
+          constexpr int NW = BM25_THREADS / 32;
+          if (warp < total) {
+            uint4 dA = make_uint4(0, 0, 0, 0), dB = dA;
+            int4 iA = make_int4(0, 0, 0, 0), iB = iA;
+            int offA = 0, loA = 0, lenA = 0, offB = 0, loB = 0, lenB = 0;
+            int c = warp;
+            fetch(c, dA, iA, offA, loA, lenA);
+            for (;;) {
+              const bool more_b = c + NW < total;
+              if (more_b) fetch(c + NW, dB, iB, offB, loB, lenB);
+              add_chunk(dA, iA, offA, loA, lenA);
+              if (!more_b) break;
+              c += NW;
+              const bool more_a = c + NW < total;
+              if (more_a) fetch(c + NW, dA, iA, offA, loA, lenA);
+              add_chunk(dB, iB, offB, loB, lenB);
+              if (!more_a) break;
+              c += NW;
+            }
           }
         }
         __syncthreads();  // all postings of this chunk of terms are in; the staging arrays may be rewritten
