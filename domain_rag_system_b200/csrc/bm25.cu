@@ -124,20 +124,42 @@ __device__ __forceinline__ void bm25_dense_sweep(int4* __restrict__ dst, const i
       }
     }
   };
-  for (int i = tid; i < T8; i += 2 * BM25_THREADS) {
-    uint4 a[NG], b[NG];
+  // Software pipeline: the next iteration's 2*NG loads are issued as soon as this iteration's rows are folded into
+  // two packed words, so the unpack / accumulate / store work of one iteration hides the L2 latency of the next.
+  // (Three and four rows in flight twice over do not fit the 64-register budget: those sweeps load per iteration.)
+  constexpr bool PIPE = NG <= 2;
+  uint4 a[NG], b[NG];
+  if (PIPE) {
 #pragma unroll
     for (int k = 0; k < NG; ++k) {
-      a[k] = __ldg(r[k] + i);
-      b[k] = __ldg(r[k] + i + BM25_THREADS);
+      a[k] = __ldg(r[k] + tid);
+      b[k] = __ldg(r[k] + tid + BM25_THREADS);
     }
+  }
+  for (int i = tid; i < T8; i += 2 * BM25_THREADS) {
+    if (!PIPE) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        a[k] = __ldg(r[k] + i);
+        b[k] = __ldg(r[k] + i + BM25_THREADS);
+      }
+    }
+    uint4 wa = a[0], wb = b[0];
 #pragma unroll
     for (int k = 1; k < NG; ++k) {
-      a[0].x += a[k].x; a[0].y += a[k].y; a[0].z += a[k].z; a[0].w += a[k].w;
-      b[0].x += b[k].x; b[0].y += b[k].y; b[0].z += b[k].z; b[0].w += b[k].w;
+      wa.x += a[k].x; wa.y += a[k].y; wa.z += a[k].z; wa.w += a[k].w;
+      wb.x += b[k].x; wb.y += b[k].y; wb.z += b[k].z; wb.w += b[k].w;
     }
-    finish(a[0], i);
-    finish(b[0], i + BM25_THREADS);
+    const int in = i + 2 * BM25_THREADS;
+    if (PIPE && in < T8) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        a[k] = __ldg(r[k] + in);
+        b[k] = __ldg(r[k] + in + BM25_THREADS);
+      }
+    }
+    finish(wa, i);
+    finish(wb, i + BM25_THREADS);
   }
 }
 
@@ -413,8 +435,10 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           for (int i = tid; i < T / 4; i += BM25_THREADS) dst[i] = make_int4(0, 0, 0, 0);
           tile_init = true;
         }
-        __syncthreads();   // the tile is initialised: atomics from any warp may follow
-        if (tid == 0) s_note[par ^ 1] = 0;
+        // The barrier that separates the plain stores of pass A from the atomics of pass B sits AFTER the first
+        // chunk's loads are issued (they read global memory only), so the wait for the slowest warp and the L2
+        // latency of the postings overlap.
+        if (nstaged <= 0) __syncthreads();
         // -- pass B: postings-list terms.  Rounds of 32 staged terms; inside a round the terms' postings are
         // cut into chunks of 128 (aligned groups of four per lane) and the warps take chunks round-robin.
         for (int r0 = 0; r0 < nstaged; r0 += 32) {
@@ -503,12 +527,16 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             }
           };
           constexpr int NW = BM25_THREADS / 32;
+          uint4 dA = make_uint4(0, 0, 0, 0), dB = dA;
+          int4 iA = make_int4(0, 0, 0, 0), iB = iA;
+          int offA = 0, loA = 0, lenA = 0, offB = 0, loB = 0, lenB = 0;
+          int c = warp;
+          if (warp < total) fetch(c, dA, iA, offA, loA, lenA);
+          if (r0 == 0) {
+            __syncthreads();   // the tile is initialised: atomics from any warp may follow
+            if (tid == 0) s_note[par ^ 1] = 0;
+          }
           if (warp < total) {
-            uint4 dA = make_uint4(0, 0, 0, 0), dB = dA;
-            int4 iA = make_int4(0, 0, 0, 0), iB = iA;
-            int offA = 0, loA = 0, lenA = 0, offB = 0, loB = 0, lenB = 0;
-            int c = warp;
-            fetch(c, dA, iA, offA, loA, lenA);
             for (;;) {
               const bool more_b = c + NW < total;
               if (more_b) fetch(c + NW, dB, iB, offB, loB, lenB);

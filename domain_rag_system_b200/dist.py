@@ -11,12 +11,16 @@ The whole step is stream-ordered on the current stream and can be captured in a 
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
+
+
+_SIDE_STREAM = os.environ.get("DRS_LATENCY_SIDE_STREAM", "0") == "1"
 
 
 def shard_bounds(n_total: int, world: int, rank: int) -> Tuple[int, int]:
@@ -100,10 +104,11 @@ class ShardedHybridSearcher:
         flags = self._buffers(nq, kprime)["flags"]
         kv = min(kprime, self.rows.shape[0])
         kb = min(kprime, self.bm25.n_docs)
-        # Latency mode (a handful of queries): the dense side is one HBM-bound streaming pass that leaves most issue
-        # slots idle, so BM25 runs beside it on a second stream.  (Not for batches: the tensor kernel needs every SM.)
+        # Experiment hook (DRS_LATENCY_SIDE_STREAM=1): in latency mode run BM25 beside the HBM-bound dense pass on a
+        # second stream.  Measured SLOWER on B200 (p50 3.3 -> 4.4 ms: the streaming kernel's statically partitioned
+        # CTAs lose their SM slots to the BM25 CTAs and finish in two waves), so it is off by default.
         side = None
-        if nq <= 8 and kb == kprime:
+        if _SIDE_STREAM and nq <= 8 and kb == kprime:
             if self._side is None:
                 self._side = torch.cuda.Stream()
             side = self._side
