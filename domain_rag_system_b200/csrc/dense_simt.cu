@@ -19,15 +19,6 @@ constexpr int SIMT_WARPS = 8;
 constexpr int SIMT_THREADS = SIMT_WARPS * 32;
 constexpr int SIMT_SORT_BUF = 2048;  // >= next_pow2(SIMT_WARPS * cand_len(DRS_MAX_KPRIME))
 
-// streaming 16-byte load: read-only path, no L1 allocation (every corpus byte is read exactly once)
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-
 __device__ __forceinline__ void warp_argmin(const uint64_t* lst, int kk, int lane, uint64_t& mk, int& mp) {
   uint64_t bk = ~0ull;
   int bp = 0;
@@ -122,16 +113,15 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
     const int64_t r_begin = int64_t(blockIdx.x) * rows_per_cta;
     const int64_t r_end = min(n_rows, r_begin + rows_per_cta);
 
-    auto load_row = [&](int64_t r, uint4 (&w)[NCH], float& nrm) {
+    auto load_row = [&](int64_t r, uint4 (&w)[NCH]) {
       const uint4* rp = reinterpret_cast<const uint4*>(corpus + size_t(r) * dim);
   #pragma unroll
       for (int ch = 0; ch < NCH; ++ch) {
         const int e = ch * 256 + lane * 8;
-        w[ch] = (e < dim) ? ldg_stream(rp + (e >> 3)) : make_uint4(0, 0, 0, 0);
+        w[ch] = (e < dim) ? __ldg(rp + (e >> 3)) : make_uint4(0, 0, 0, 0);
       }
-      nrm = __ldg(inv_norm + r);   // travels with the row: no dependent load at scoring time
     };
-    auto score_row = [&](int64_t r, const uint4 (&w)[NCH], const float nrm) {
+    auto score_row = [&](int64_t r, const uint4 (&w)[NCH]) {
       if (mask != nullptr && mask[r] == 0) return;
       float acc[QT];
   #pragma unroll
@@ -153,6 +143,7 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
           acc[j] = fmaf(c7, qq[7], acc[j]);
         }
       }
+      const float nrm = __ldg(inv_norm + r);
   #pragma unroll
       for (int j = 0; j < QT; ++j) {
         float a = acc[j];
@@ -176,43 +167,35 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
       }
     };
 
+    // rows in flight per warp: four when the queries leave registers for it (latency mode: the kernel is
+    // purely HBM-bound and needs ~64 KB of loads outstanding per SM), else two.  (A rolling window that issues a
+    // row's loads three rows ahead of its scoring, with L1::no_allocate loads, measured SLOWER: 4.06 vs 2.79 ms
+    // at 10 M x 768 -- the batch of twelve 16-byte loads per warp is what keeps HBM busy.)
     int64_t r = r_begin + warp;
     if (QT <= 2) {
-      // Latency mode: the kernel is purely HBM-bound, so every warp keeps a rolling window of three to four rows
-      // in flight -- a row's loads are issued three rows before it is scored, and the window never drains between
-      // iterations (the earlier load-4 / score-4 loop left a warp with nothing outstanding while it scored).
-      const int64_t n_my = r < r_end ? (r_end - r + SIMT_WARPS - 1) / SIMT_WARPS : 0;
-      auto row_at = [&](int64_t i) { return r + i * SIMT_WARPS; };
-      uint4 w0[NCH], w1[NCH], w2[NCH], w3[NCH];
-      float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-      if (0 < n_my) load_row(row_at(0), w0, n0);
-      if (1 < n_my) load_row(row_at(1), w1, n1);
-      if (2 < n_my) load_row(row_at(2), w2, n2);
-      for (int64_t i = 0; i < n_my; i += 4) {
-        if (i + 3 < n_my) load_row(row_at(i + 3), w3, n3);
-        score_row(row_at(i), w0, n0);
-        if (i + 4 < n_my) load_row(row_at(i + 4), w0, n0);
-        if (i + 1 < n_my) score_row(row_at(i + 1), w1, n1);
-        if (i + 5 < n_my) load_row(row_at(i + 5), w1, n1);
-        if (i + 2 < n_my) score_row(row_at(i + 2), w2, n2);
-        if (i + 6 < n_my) load_row(row_at(i + 6), w2, n2);
-        if (i + 3 < n_my) score_row(row_at(i + 3), w3, n3);
+      for (; r + 3 * SIMT_WARPS < r_end; r += 4 * SIMT_WARPS) {
+        uint4 w0[NCH], w1[NCH], w2[NCH], w3[NCH];
+        load_row(r, w0);
+        load_row(r + SIMT_WARPS, w1);
+        load_row(r + 2 * SIMT_WARPS, w2);
+        load_row(r + 3 * SIMT_WARPS, w3);
+        score_row(r, w0);
+        score_row(r + SIMT_WARPS, w1);
+        score_row(r + 2 * SIMT_WARPS, w2);
+        score_row(r + 3 * SIMT_WARPS, w3);
       }
-    } else {
-      for (; r + SIMT_WARPS < r_end; r += 2 * SIMT_WARPS) {
-        uint4 w0[NCH], w1[NCH];
-        float n0, n1;
-        load_row(r, w0, n0);
-        load_row(r + SIMT_WARPS, w1, n1);
-        score_row(r, w0, n0);
-        score_row(r + SIMT_WARPS, w1, n1);
-      }
-      if (r < r_end) {
-        uint4 w0[NCH];
-        float n0;
-        load_row(r, w0, n0);
-        score_row(r, w0, n0);
-      }
+    }
+    for (; r + SIMT_WARPS < r_end; r += 2 * SIMT_WARPS) {
+      uint4 w0[NCH], w1[NCH];
+      load_row(r, w0);
+      load_row(r + SIMT_WARPS, w1);
+      score_row(r, w0);
+      score_row(r + SIMT_WARPS, w1);
+    }
+    if (r < r_end) {
+      uint4 w0[NCH];
+      load_row(r, w0);
+      score_row(r, w0);
     }
     __syncthreads();
 
