@@ -30,6 +30,9 @@
 // (2-byte head-term rows shared by all queries through L2), so its practical bound is issue slots, shared-memory
 // atomics and the per-phase latency of every (tile, query) pair, not HBM.
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -92,11 +95,12 @@ __device__ __forceinline__ void smem_red_add_s32(uint32_t addr, int v) {
 // NG head-term rows are summed as packed 16-bit lanes and added to the score tile, two 16-byte groups (16
 // documents) per thread and iteration, all 2*NG loads issued before the first use.  ACC = the tile already holds
 // this query's sums (second and later sweeps); CROSS = note the documents a sweep takes across the threshold.
-// Specialised so that the loop carries no per-row predicates: ~36 instructions per group of 8 documents.
-template <int NG, bool ACC, bool CROSS, class NoteFn>
+// Specialised on NG so that the loop carries no per-row predicates: ~40 instructions per group of 8 documents
+// (98 in the general loop it replaces).
+template <int NG, bool CROSS, class NoteFn>
 __device__ __forceinline__ void bm25_dense_sweep(int4* __restrict__ dst, const int T8, const uint16_t* const* rowp,
                                                  const int64_t doc0, const int mul, const int tau_s0, const int tid,
-                                                 NoteFn&& note) {
+                                                 const bool ACC, NoteFn&& note) {
   const uint4* r[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) r[k] = reinterpret_cast<const uint4*>(rowp[k] + doc0);
@@ -114,12 +118,21 @@ __device__ __forceinline__ void bm25_dense_sweep(int4* __restrict__ dst, const i
     dst[T8 + i] = hi4;
     if (CROSS) {
       if (max(max(max(lo4.x, lo4.y), max(lo4.z, lo4.w)), max(max(hi4.x, hi4.y), max(hi4.z, hi4.w))) >= tau_s0) {
+        // rare: which of my eight documents did THIS sweep take across the threshold?  (one note() site: the
+        // kernel is instruction-cache sensitive)
         const int nv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
         const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+        unsigned hit = 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int cv = int((u & 1) ? (ws[u >> 1] >> 16) : (ws[u >> 1] & 0xffffu)) * mul;   // this sweep's share
-          if (nv[u] >= tau_s0 && nv[u] - cv < tau_s0) note((u < 4 ? 0 : 4 * T8) + 4 * i + (u & 3));
+          hit |= (nv[u] >= tau_s0 && nv[u] - cv < tau_s0) ? (1u << u) : 0u;
+        }
+#pragma unroll 1
+        while (hit) {
+          const int u = __ffs(hit) - 1;
+          hit &= hit - 1;
+          note((u < 4 ? 0 : 4 * T8) + 4 * i + (u & 3));
         }
       }
     }
@@ -173,7 +186,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
     unsigned long long* __restrict__ gtau, const int32_t* __restrict__ flags, const int32_t* __restrict__ fx_low,
-    int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids, int* __restrict__ next_query) {
+    int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids, int* __restrict__ next_query,
+    unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
   Pair64* pbuf = reinterpret_cast<Pair64*>(smem_raw);                    // EXACT: [BM25_MBUF / 2] (score, doc) pairs
@@ -319,6 +333,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       // is read by every thread after tile j's last barrier while the early threads may already be noting for
       // tile j+1 -- in the other counter.  Thread 0 clears a counter one tile after its use.
       par ^= 1;
+      // DRS_BM25_TRACE (debugging aid): clock of CTA 0 / thread 0 at the phase boundaries of its first 400 tiles
+      auto mark = [&](int k) {
+        if (trace != nullptr && blockIdx.x == 0 && tid == 0) {
+          const unsigned long long n = trace[0];
+          if (n < 400) trace[1 + n * 6 + k] = clock64();
+          if (k == 5) trace[0] = n + 1;
+        }
+      };
+      mark(0);
       auto note = [&](int dl) {
         const int pos = cnt_list + atomicAdd(&s_note[par], 1);
         if (pos < cap) mbuf[kk + pos] = uint64_t(dl);
@@ -367,9 +390,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           if (cross && max(max(max(lo4.x, lo4.y), max(lo4.z, lo4.w)), max(max(hi4.x, hi4.y), max(hi4.z, hi4.w))) >= tau_s0) {
             const int nv[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
             const int cv[8] = {cl.x, cl.y, cl.z, cl.w, ch.x, ch.y, ch.z, ch.w};
+            unsigned hit = 0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (nv[u] >= tau_s0 && nv[u] - cv[u] < tau_s0) note((u < 4 ? 0 : T / 2) + 4 * i + (u & 3));
+            for (int u = 0; u < 8; ++u) hit |= (nv[u] >= tau_s0 && nv[u] - cv[u] < tau_s0) ? (1u << u) : 0u;
+#pragma unroll 1
+            while (hit) {
+              const int u = __ffs(hit) - 1;
+              hit &= hit - 1;
+              note((u < 4 ? 0 : T / 2) + 4 * i + (u & 3));
+            }
           }
         };
         // Fast path: full-size tiles and rows at least as coarse as the score unit (every benchmark shape).  The
@@ -382,13 +411,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           const uint16_t* const* rp = s_rowp + g0;
 #define DRS_SWEEP(NG_)                                                                                 \
   do {                                                                                                 \
-    if (cross) {                                                                                       \
-      if (tile_init) bm25_dense_sweep<NG_, true, true>(dst, T8, rp, doc0, mul, tau_s0, tid, note);     \
-      else bm25_dense_sweep<NG_, false, true>(dst, T8, rp, doc0, mul, tau_s0, tid, note);              \
-    } else {                                                                                           \
-      if (tile_init) bm25_dense_sweep<NG_, true, false>(dst, T8, rp, doc0, mul, tau_s0, tid, note);    \
-      else bm25_dense_sweep<NG_, false, false>(dst, T8, rp, doc0, mul, tau_s0, tid, note);             \
-    }                                                                                                  \
+    if (cross) bm25_dense_sweep<NG_, true>(dst, T8, rp, doc0, mul, tau_s0, tid, tile_init, note);      \
+    else bm25_dense_sweep<NG_, false>(dst, T8, rp, doc0, mul, tau_s0, tid, tile_init, note);           \
   } while (0)
           if (ng == 4) DRS_SWEEP(4);
           else if (ng == 3) DRS_SWEEP(3);
@@ -439,6 +463,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         // chunk's loads are issued (they read global memory only), so the wait for the slowest warp and the L2
         // latency of the postings overlap.
         if (nstaged <= 0) __syncthreads();
+        mark(1);
         // -- pass B: postings-list terms.  Rounds of 32 staged terms; inside a round the terms' postings are
         // cut into chunks of 128 (aligned groups of four per lane) and the warps take chunks round-robin.
         for (int r0 = 0; r0 < nstaged; r0 += 32) {
@@ -499,11 +524,15 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
                 const int b2 = smem_atom_add_s32(sc_rel + 4u * d.z, im.z), b3 = smem_atom_add_s32(sc_rel + 4u * d.w, im.w);
                 const bool c0 = unsigned(taum1 - b0) < unsigned(im.x), c1 = unsigned(taum1 - b1) < unsigned(im.y);
                 const bool c2 = unsigned(taum1 - b2) < unsigned(im.z), c3 = unsigned(taum1 - b3) < unsigned(im.w);
-                if (c0 | c1 | c2 | c3) {
-                  if (c0) note(int(d.x - d0u));
-                  if (c1) note(int(d.y - d0u));
-                  if (c2) note(int(d.z - d0u));
-                  if (c3) note(int(d.w - d0u));
+                unsigned hit = (c0 ? 1u : 0u) | (c1 ? 2u : 0u) | (c2 ? 4u : 0u) | (c3 ? 8u : 0u);
+                if (hit) {
+                  const uint32_t ds[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll 1
+                  while (hit) {
+                    const int u = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    note(int((u == 0 ? ds[0] : u == 1 ? ds[1] : u == 2 ? ds[2] : ds[3]) - d0u));
+                  }
                 }
               } else {
                 smem_red_add_s32(sc_rel + 4u * d.x, im.x);
@@ -512,18 +541,20 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
                 smem_red_add_s32(sc_rel + 4u * d.w, im.w);
               }
             } else {   // a term's first or last group
-              auto add1 = [&](uint32_t doc, int v) {
+              const uint32_t ds[4] = {d.x, d.y, d.z, d.w};
+              const int vs[4] = {im.x, im.y, im.z, im.w};
+#pragma unroll 1
+              for (int u = 0; u < 4; ++u) {
+                if (off + u < slo || off + u >= slen) continue;
+                const uint32_t doc = u == 0 ? ds[0] : u == 1 ? ds[1] : u == 2 ? ds[2] : ds[3];
+                const int v = u == 0 ? vs[0] : u == 1 ? vs[1] : u == 2 ? vs[2] : vs[3];
                 if (cross) {
                   const int before = smem_atom_add_s32(sc_rel + 4u * doc, v);
                   if (unsigned(taum1 - before) < unsigned(v)) note(int(doc - d0u));
                 } else {
                   smem_red_add_s32(sc_rel + 4u * doc, v);
                 }
-              };
-              if (off >= slo) add1(d.x, im.x);
-              if (off + 1 >= slo && off + 1 < slen) add1(d.y, im.y);
-              if (off + 2 >= slo && off + 2 < slen) add1(d.z, im.z);
-              if (off + 3 >= slo && off + 3 < slen) add1(d.w, im.w);
+              }
             }
           };
           constexpr int NW = BM25_THREADS / 32;
@@ -535,6 +566,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           if (r0 == 0) {
             __syncthreads();   // the tile is initialised: atomics from any warp may follow
             if (tid == 0) s_note[par ^ 1] = 0;
+            mark(2);
           }
           if (warp < total) {
             for (;;) {
@@ -551,7 +583,9 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             }
           }
         }
+        mark(3);
         __syncthreads();  // all postings of this chunk of terms are in; the staging arrays may be rewritten
+        mark(4);
       }
       if (!tile_init) {   // query without terms: every score is 0
         for (int i = tid; i < T / 4; i += BM25_THREADS) reinterpret_cast<int4*>(sc)[i] = make_int4(0, 0, 0, 0);
@@ -672,6 +706,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           maybe_merge(cold, (done >= T) && (j == tile_lo));
         }
       }
+      mark(5);
     }
     if constexpr (EXACT) {
       for (int i = tid; i < kprime; i += BM25_THREADS) {
@@ -897,12 +932,36 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
   DRS_ENSURE_SMEM((bm25_select_kernel<false>), smem);
   DRS_ENSURE_SMEM((bm25_select_kernel<true>), smem);
+  // DRS_BM25_TRACE=1 (debugging aid, synchronises): phase timeline of CTA 0 on stderr
+  static const bool want_trace = getenv("DRS_BM25_TRACE") != nullptr;
+  static unsigned long long* d_trace = nullptr;
+  if (want_trace) {
+    if (!d_trace) cudaMalloc(&d_trace, (1 + 400 * 6) * sizeof(unsigned long long));
+    cudaMemsetAsync(d_trace, 0, (1 + 400 * 6) * sizeof(unsigned long long), st);
+  }
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
     bm25_select_kernel<false><<<gy, BM25_THREADS, smem, st>>>(
         ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr,
-        next_query);
+        next_query, want_trace ? d_trace : nullptr);
     count_launches(1);
+  }
+  if (want_trace) {
+    static int dumps = 0;
+    std::vector<unsigned long long> h(1 + 400 * 6);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (dumps++ == 3) {   // a warm call
+      const int n = int(h[0] < 400 ? h[0] : 400);
+      double ph[5] = {0, 0, 0, 0, 0}, gap = 0;
+      for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 5; ++k) ph[k] += double(h[1 + i * 6 + k + 1] - h[1 + i * 6 + k]);
+        if (i) gap += double(h[1 + i * 6] - h[1 + (i - 1) * 6 + 5]);
+      }
+      fprintf(stderr, "[bm25 trace] %d tiles of CTA 0, cycles per tile: passA %.0f | barrier1(+fetch) %.0f | passB %.0f | "
+                      "barrier2 %.0f | select %.0f | between tiles %.0f\n", n, ph[0] / n, ph[1] / n, ph[2] / n, ph[3] / n,
+              ph[4] / n, gap / (n > 1 ? n - 1 : 1));
+    }
   }
   DRS_CUDA_CHECK(cudaGetLastError());
   ProfScope pt(DRS_PROF_BM25_TAIL, st);
@@ -916,7 +975,7 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
     // escalation, predicated on the device-side flags (no host round trip): CTAs of proven queries exit at once
     bm25_select_kernel<true><<<gy, BM25_THREADS, smem, st>>>(
         ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
-        next_query + 1);
+        next_query + 1, nullptr);
     count_launches(1);
     DRS_CUDA_CHECK(cudaGetLastError());
     rc = launch_merge_pairs_f64(escores, eids, gx, n_queries, kprime, kprime, d_out_scores, d_out_ids, flags, st);
