@@ -498,8 +498,11 @@ def run_ours(args):
                      "algorithmic_gbs_8B_per_posting": 8.0 * sum_df / (b_launch / 1e3) / 1e9 if b_ms > 0 else 0.0,
                      "note": "bytes = every posting list (8 B/posting) or packed head-term row (2 B/document) the batch "
                              "touches, counted ONCE: the 1000 queries share them through L2, so this is what must leave "
-                             "HBM.  The kernel is nowhere near this bound: it is issue-bound (profiles/: ~70 % issue "
-                             "slots active, ~12 thread-instructions per posting visited)."}
+                             "HBM.  The kernel is nowhere near this bound: it is bound by the dependent latency chain of a "
+                             "(tile, query) pass -- two L2 round trips for the head-term rows, one for the postings, "
+                             "shared-memory atomics, three block barriers, ~11.4 k cycles per 8192 documents with four "
+                             "CTAs per SM (profiles/r2t_summary.txt; cutting its instructions by 24 % did not move "
+                             "its time)."}
     roofline_bm25["frac"] = roofline_bm25["achieved"] / peaks["hbm_gbs"]
     breakdown = {k: (v[0] / args.steps) for k, v in prof.items()}
 

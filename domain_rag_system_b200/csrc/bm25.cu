@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     if (n <= BM25_THREADS) {
       // Small merges (the common case: a few dozen survivors) rank by counting -- keys are distinct, so an
       // element's rank is the number of larger keys: three barriers instead of a 28..36-stage sorting network.
+      // (Sharing a key's comparisons among 256 / n adjacent threads and dropping one barrier was measured: no
+      // gain, 1.309 vs 1.296 ms in an in-process A/B -- the merge is not what the CTA waits for.)
       const uint64_t key = tid < n ? mbuf[tid] : 0;
       int rank = 0;
       if (key != 0)
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     if (tid == 0) {
       s_cnt = 0;
       unsigned long long t = mbuf[kk - 1];  // 0 while the list is not full
-      if (t) atomicMax(gtau + q, t);
-      const unsigned long long g = *reinterpret_cast<volatile unsigned long long*>(gtau + q);
+      // one global round trip: the atomic's return value is the other CTAs' best so far
+      const unsigned long long g = t ? atomicMax(gtau + q, t) : *reinterpret_cast<volatile unsigned long long*>(gtau + q);
       s_tau = t > g ? t : g;
     }
     __syncthreads();
@@ -337,8 +339,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
       auto mark = [&](int k) {
         if (trace != nullptr && blockIdx.x == 0 && tid == 0) {
           const unsigned long long n = trace[0];
-          if (n < 400) trace[1 + n * 6 + k] = clock64();
-          if (k == 5) trace[0] = n + 1;
+          if (n < 400) trace[1 + n * 7 + k] = clock64();
+          if (k == 6) trace[0] = n + 1;
         }
       };
       mark(0);
@@ -654,6 +656,10 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         auto maybe_merge = [&](bool cold, bool last) {
           const int cnt = cnt_list;
           if (cnt > 0 && (last || cnt > cap / 2 || cnt >= BM25_MERGE_AT || ((cold || seen < 4ll * T) && cnt >= kk))) {
+            if (trace != nullptr && blockIdx.x == 0 && tid == 0) {
+              trace[2 + 400 * 7] += 1;
+              trace[3 + 400 * 7] += unsigned(kk + cnt);
+            }
             merge(q, cnt);
             cnt_list = 0;
           }
@@ -670,9 +676,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
               }
               __syncthreads();
             }
+            if (trace != nullptr && blockIdx.x == 0 && tid == 0) trace[1 + 400 * 7] += unsigned(cnt_now - cnt_list);
             cnt_list = cnt_now;
             done = T;
             seen += T;
+            mark(5);
             maybe_merge(false, j == tile_lo);
           }
         }
@@ -706,7 +714,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           maybe_merge(cold, (done >= T) && (j == tile_lo));
         }
       }
-      mark(5);
+      mark(6);
     }
     if constexpr (EXACT) {
       for (int i = tid; i < kprime; i += BM25_THREADS) {
@@ -936,8 +944,8 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   static const bool want_trace = getenv("DRS_BM25_TRACE") != nullptr;
   static unsigned long long* d_trace = nullptr;
   if (want_trace) {
-    if (!d_trace) cudaMalloc(&d_trace, (1 + 400 * 6) * sizeof(unsigned long long));
-    cudaMemsetAsync(d_trace, 0, (1 + 400 * 6) * sizeof(unsigned long long), st);
+    if (!d_trace) cudaMalloc(&d_trace, (1 + 400 * 7 + 4) * sizeof(unsigned long long));
+    cudaMemsetAsync(d_trace, 0, (1 + 400 * 7 + 4) * sizeof(unsigned long long), st);
   }
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
@@ -948,19 +956,31 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   }
   if (want_trace) {
     static int dumps = 0;
-    std::vector<unsigned long long> h(1 + 400 * 6);
+    std::vector<unsigned long long> h(1 + 400 * 7 + 4);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     if (dumps++ == 3) {   // a warm call
       const int n = int(h[0] < 400 ? h[0] : 400);
-      double ph[5] = {0, 0, 0, 0, 0}, gap = 0;
+      double ph[6] = {0, 0, 0, 0, 0, 0}, gap = 0;
+      int crossing = 0;
       for (int i = 0; i < n; ++i) {
-        for (int k = 0; k < 5; ++k) ph[k] += double(h[1 + i * 6 + k + 1] - h[1 + i * 6 + k]);
-        if (i) gap += double(h[1 + i * 6] - h[1 + (i - 1) * 6 + 5]);
+        const unsigned long long* t = &h[1 + i * 7];
+        const bool cr = t[5] != 0;                  // mark 5 is only reached in crossing mode
+        crossing += cr;
+        for (int k = 0; k < 4; ++k) ph[k] += double(t[k + 1] - t[k]);
+        if (cr) {
+          ph[4] += double(t[5] - t[4]);
+          ph[5] += double(t[6] - t[5]);
+        } else {
+          ph[5] += double(t[6] - t[4]);
+        }
+        if (i) gap += double(t[0] - h[1 + (i - 1) * 7 + 6]);
       }
-      fprintf(stderr, "[bm25 trace] %d tiles of CTA 0, cycles per tile: passA %.0f | barrier1(+fetch) %.0f | passB %.0f | "
-                      "barrier2 %.0f | select %.0f | between tiles %.0f\n", n, ph[0] / n, ph[1] / n, ph[2] / n, ph[3] / n,
-              ph[4] / n, gap / (n > 1 ? n - 1 : 1));
+      fprintf(stderr, "[bm25 trace] noted documents %llu, merges %llu (mean size %.0f keys)\n", h[1 + 400 * 7], h[2 + 400 * 7],
+              h[2 + 400 * 7] ? double(h[3 + 400 * 7]) / double(h[2 + 400 * 7]) : 0.0);
+      fprintf(stderr, "[bm25 trace] %d tiles of CTA 0 (%d in crossing mode), cycles per tile: passA %.0f | barrier1(+fetch) "
+                      "%.0f | passB %.0f | barrier2 %.0f | noted->keys %.0f | merge/scan %.0f | between tiles %.0f\n", n,
+              crossing, ph[0] / n, ph[1] / n, ph[2] / n, ph[3] / n, ph[4] / n, ph[5] / n, gap / (n > 1 ? n - 1 : 1));
     }
   }
   DRS_CUDA_CHECK(cudaGetLastError());
