@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
     unsigned long long* __restrict__ gtau, const int32_t* __restrict__ flags, const int32_t* __restrict__ fx_low,
     int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids, int* __restrict__ next_query,
-    unsigned long long* __restrict__ trace) {
+    unsigned long long* __restrict__ trace, int dbg) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
   Pair64* pbuf = reinterpret_cast<Pair64*>(smem_raw);                    // EXACT: [BM25_MBUF / 2] (score, doc) pairs
@@ -365,7 +365,9 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           tp0 = __ldg(tp);
           tp1 = __ldg(tp + 1);
         }
-        const int nd = s_nd;
+        // dbg (DRS_BM25_DEBUG, timing experiments only -- results are garbage): 1 no head-term rows, 2 no postings
+        // pass, 4 postings fetched but not added, 8 no selection
+        const int nd = (dbg & 1) ? 0 : s_nd;
         // -- pass A: dense rows (packed 14-bit values, 8 documents per 16-byte load), up to four rows summed as
         // packed 16-bit lanes per sweep; the first sweep also initialises the tile.  16-byte group i of a row
         // holds documents 4i..4i+3 of the tile's first half and 4i..4i+3 of its second half, so a thread's two
@@ -468,7 +470,11 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
         mark(1);
         // -- pass B: postings-list terms.  Rounds of 32 staged terms; inside a round the terms' postings are
         // cut into chunks of 128 (aligned groups of four per lane) and the warps take chunks round-robin.
-        for (int r0 = 0; r0 < nstaged; r0 += 32) {
+        if (dbg & 2) {
+          __syncthreads();
+          if (tid == 0) s_note[par ^ 1] = 0;
+        }
+        for (int r0 = 0; r0 < ((dbg & 2) ? 0 : nstaged); r0 += 32) {
           if (r0 > 0) {   // rounds after the first fetch their ranges here
             tp0 = tp1 = 0;
             if (r0 + lane < nstaged && s_base[r0 + lane] >= 0) {
@@ -518,6 +524,10 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
           const int taum1 = tau_s0 - 1;
           auto add_chunk = [&](const uint4 d, int4 im, const int off, const int slo, const int slen) {
             if (off >= slen) return;
+            if (dbg & 4) {
+              if ((d.x ^ d.y ^ d.z ^ d.w ^ unsigned(im.x ^ im.y ^ im.z ^ im.w)) == 0x9e3779b9u) s_cnt = 1;   // keeps the loads
+              return;
+            }
             im.x >>= sh; im.y >>= sh; im.z >>= sh; im.w >>= sh;
             if (off >= slo && off + 3 < slen) {   // all four postings are the term's: no per-posting predicates
               if (cross) {
@@ -664,8 +674,8 @@ __global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
             cnt_list = 0;
           }
         };
-        int done = 0;
-        if (cross) {
+        int done = (dbg & 8) ? T : 0;
+        if (cross && !(dbg & 8)) {
           const int cnt_now = cnt_list + s_note[par];   // the accumulation ended with a barrier
           if (cnt_now <= cap) {        // (else: more crossings than the append area holds -- scan the ordinary way)
             if (cnt_now > cnt_list) {  // noted documents -> keys, with their FINAL scores
@@ -874,6 +884,12 @@ static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& n_c
 
 using namespace drs;
 
+// DRS_BM25_DEBUG: timing experiments (see the kernel); read on every call so that one process can compare variants
+static int bm25_debug_flags() {
+  const char* e = getenv("DRS_BM25_DEBUG");
+  return e ? atoi(e) : 0;
+}
+
 // workspace layout (bytes): parts | cand | gtau | merge scratch | flags | fx_low | e_scores | e_ids
 struct Bm25Ws {
   size_t parts, cand, gtau, mscratch, flags, fxlow, escores, eids, total;
@@ -951,7 +967,7 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
     bm25_select_kernel<false><<<gy, BM25_THREADS, smem, st>>>(
         ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr,
-        next_query, want_trace ? d_trace : nullptr);
+        next_query, want_trace ? d_trace : nullptr, bm25_debug_flags());
     count_launches(1);
   }
   if (want_trace) {
@@ -995,7 +1011,7 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
     // escalation, predicated on the device-side flags (no host round trip): CTAs of proven queries exit at once
     bm25_select_kernel<true><<<gy, BM25_THREADS, smem, st>>>(
         ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
-        next_query + 1, nullptr);
+        next_query + 1, nullptr, 0);
     count_launches(1);
     DRS_CUDA_CHECK(cudaGetLastError());
     rc = launch_merge_pairs_f64(escores, eids, gx, n_queries, kprime, kprime, d_out_scores, d_out_ids, flags, st);

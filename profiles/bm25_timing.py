@@ -31,6 +31,19 @@ def main():
     for _ in range(3):
         sc, ids, flags = _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws, want_flags=True)
     torch.cuda.synchronize()
+    ab = {}
+    for dbg in os.environ.get("BM25_AB", "").split(","):      # BM25_AB=0,1,2,...: DRS_BM25_DEBUG values, one after the other
+        if dbg == "":
+            continue
+        os.environ["DRS_BM25_DEBUG"] = dbg
+        _lib.profile_enable(True)
+        for _ in range(iters):
+            _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws, mode="no_escalation")
+        ab.setdefault(dbg, []).append(round(_lib.profile_read()["bm25_select"][0] / iters, 4))
+        _lib.profile_enable(False)
+    if ab:
+        print(json.dumps({"bm25_select_ms_by_debug_flags": ab}))
+        os.environ.pop("DRS_BM25_DEBUG", None)
     _lib.profile_enable(True)
     for _ in range(iters):
         _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws)
