@@ -39,7 +39,12 @@
 namespace drs {
 
 constexpr int BM25_THREADS = 256;
-constexpr int BM25_MBUF = 2048;  // merge buffer (u64 keys): list + candidate append area
+// merge buffer (u64 keys): list + candidate append area.  CPS = resident CTAs per SM the kernel is compiled for: 4 (64
+// registers, 16 KB buffer; the default) or 5 (48 registers, 8 KB buffer: 25 % more documents in flight per SM).
+// Measured at 1 M x 1000, k'=10, in one process: 3 CTAs (79 registers) 1.494 ms, 4 CTAs 1.287 ms, 5 CTAs 1.337 ms --
+// the occupancy curve is flat at the top: the SM is saturated by the mix (issue slots 56 %, LSU 56 %, latency).
+__host__ __device__ constexpr int bm25_mbuf(int cps) { return cps >= 5 ? 1024 : 2048; }
+constexpr int BM25_DEFAULT_CPS = 4;
 constexpr int BM25_TCHUNK = 64;  // query term occurrences whose posting ranges are staged per tile at once
 constexpr int BM25_SEG = 1024;   // documents scanned between overflow checks
 constexpr int BM25_MERGE_AT = 192;  // survivors that justify a re-sort (warm list): list + survivors fit a 256-sort
@@ -181,13 +186,14 @@ __device__ __forceinline__ void bm25_dense_sweep(int4* __restrict__ dst, const i
 //   same accumulation, but EVERY document whose integer score reaches fx_low[q] -- the smallest integer score
 //   a member of the true top-k' can have, see bm25_rescore_kernel -- is re-scored exactly on the spot and the
 //   exact (score, doc) top-k' of the slice is kept.
-template <bool EXACT>
-__global__ void __launch_bounds__(BM25_THREADS, 4) bm25_select_kernel(
+template <bool EXACT, int CPS>
+__global__ void __launch_bounds__(BM25_THREADS, CPS) bm25_select_kernel(
     drs_bm25_index ix, const int32_t* __restrict__ q_terms, const int32_t* __restrict__ q_offsets,
     int n_queries, int kk, int tiles_per_cta, uint64_t* __restrict__ parts, int q_stride,
     unsigned long long* __restrict__ gtau, const int32_t* __restrict__ flags, const int32_t* __restrict__ fx_low,
     int kprime, double* __restrict__ e_scores, int64_t* __restrict__ e_ids, int* __restrict__ next_query,
     unsigned long long* __restrict__ trace, int dbg) {
+  constexpr int BM25_MBUF = bm25_mbuf(CPS);
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint64_t* mbuf = reinterpret_cast<uint64_t*>(smem_raw);                // [BM25_MBUF]
   Pair64* pbuf = reinterpret_cast<Pair64*>(smem_raw);                    // EXACT: [BM25_MBUF / 2] (score, doc) pairs
@@ -863,8 +869,16 @@ __global__ void __launch_bounds__(256) bm25_rescore_kernel(drs_bm25_index ix, co
 // short enough (<= 32 tiles) for a slice's rows and postings to stay in L2 while all queries pass over it, and
 // numerous enough that a small batch still spreads over the GPU (a single query: one tile per item).
 // n_ctas persistent CTAs pull items from a counter.
+// Resident CTAs per SM the selection kernel runs with (see bm25_mbuf): DRS_BM25_CTAS=4|5 overrides, read on every
+// call so that one process can compare (workspace sizing and launch see the same value).
+static int bm25_cps() {
+  const char* e = getenv("DRS_BM25_CTAS");
+  const int v = e ? atoi(e) : BM25_DEFAULT_CPS;
+  return v >= 5 ? 5 : 4;
+}
+
 static void bm25_grid(const drs_bm25_index* ix, int n_queries, int& gx, int& n_ctas, int& tiles_per_cta) {
-  const int target = 4 * sm_count();
+  const int target = bm25_cps() * sm_count();
   const int q = n_queries > 0 ? n_queries : 1;
   const int gx_l2 = (ix->n_tiles + 31) / 32;        // L2 locality
   int gx_par = (8 * target + q - 1) / q;             // ~8 items per resident CTA
@@ -953,9 +967,15 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   int64_t* eids = reinterpret_cast<int64_t*>(base + w.eids);
   int* next_query = reinterpret_cast<int*>(gtau + n_queries);   // [2]: one counter per pass
   DRS_CUDA_CHECK(cudaMemsetAsync(gtau, 0, size_t(n_queries) * 8 + 2 * 4, st));
-  const size_t smem = size_t(BM25_MBUF) * 8 + size_t(ix.tile_docs) * 4;
-  DRS_ENSURE_SMEM((bm25_select_kernel<false>), smem);
-  DRS_ENSURE_SMEM((bm25_select_kernel<true>), smem);
+  const int cps = bm25_cps();
+  const size_t smem = size_t(bm25_mbuf(cps)) * 8 + size_t(ix.tile_docs) * 4;
+  if (cps == 5) {
+    DRS_ENSURE_SMEM((bm25_select_kernel<false, 5>), smem);
+    DRS_ENSURE_SMEM((bm25_select_kernel<true, 5>), smem);
+  } else {
+    DRS_ENSURE_SMEM((bm25_select_kernel<false, 4>), smem);
+    DRS_ENSURE_SMEM((bm25_select_kernel<true, 4>), smem);
+  }
   // DRS_BM25_TRACE=1 (debugging aid, synchronises): phase timeline of CTA 0 on stderr
   static const bool want_trace = getenv("DRS_BM25_TRACE") != nullptr;
   static unsigned long long* d_trace = nullptr;
@@ -965,9 +985,14 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   }
   {
     ProfScope ps(DRS_PROF_BM25_SELECT, st);
-    bm25_select_kernel<false><<<gy, BM25_THREADS, smem, st>>>(
-        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr, nullptr,
-        next_query, want_trace ? d_trace : nullptr, bm25_debug_flags());
+    if (cps == 5)
+      bm25_select_kernel<false, 5><<<gy, BM25_THREADS, smem, st>>>(
+          ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr,
+          nullptr, next_query, want_trace ? d_trace : nullptr, bm25_debug_flags());
+    else
+      bm25_select_kernel<false, 4><<<gy, BM25_THREADS, smem, st>>>(
+          ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, parts, n_queries, gtau, nullptr, nullptr, kprime, nullptr,
+          nullptr, next_query, want_trace ? d_trace : nullptr, bm25_debug_flags());
     count_launches(1);
   }
   if (want_trace) {
@@ -1009,9 +1034,14 @@ extern "C" int drs_bm25_topk_ex(const drs_bm25_index* index, const int32_t* d_q_
   DRS_CUDA_CHECK(cudaGetLastError());
   if (mode != 1) {
     // escalation, predicated on the device-side flags (no host round trip): CTAs of proven queries exit at once
-    bm25_select_kernel<true><<<gy, BM25_THREADS, smem, st>>>(
-        ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
-        next_query + 1, nullptr, 0);
+    if (cps == 5)
+      bm25_select_kernel<true, 5><<<gy, BM25_THREADS, smem, st>>>(
+          ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
+          next_query + 1, nullptr, 0);
+    else
+      bm25_select_kernel<true, 4><<<gy, BM25_THREADS, smem, st>>>(
+          ix, d_q_terms, d_q_offsets, n_queries, kk, tpc, nullptr, n_queries, nullptr, flags, fxlow, kprime, escores, eids,
+          next_query + 1, nullptr, 0);
     count_launches(1);
     DRS_CUDA_CHECK(cudaGetLastError());
     rc = launch_merge_pairs_f64(escores, eids, gx, n_queries, kprime, kprime, d_out_scores, d_out_ids, flags, st);

@@ -44,6 +44,22 @@ def main():
     if ab:
         print(json.dumps({"bm25_select_ms_by_debug_flags": ab}))
         os.environ.pop("DRS_BM25_DEBUG", None)
+    ab = {}
+    for cps in os.environ.get("BM25_CTAS_AB", "").split(","):  # BM25_CTAS_AB=4,5,4,5: resident CTAs per SM, interleaved
+        if cps == "":
+            continue
+        os.environ["DRS_BM25_CTAS"] = cps
+        for _ in range(2):
+            out = _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws)
+        _lib.profile_enable(True)
+        for _ in range(iters):
+            _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws)
+        pr = _lib.profile_read()
+        ab.setdefault(cps, []).append((round(pr["bm25_select"][0] / iters, 4), int(out[1].sum().item())))
+        _lib.profile_enable(False)
+    if ab:
+        print(json.dumps({"bm25_select_ms_and_checksum_by_ctas_per_sm": ab}))
+        os.environ.pop("DRS_BM25_CTAS", None)
     _lib.profile_enable(True)
     for _ in range(iters):
         _lib.bm25_topk(ix.struct(), q_terms, q_offs, q, kprime, ws=ws)
