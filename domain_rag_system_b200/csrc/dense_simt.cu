@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(SIMT_THREADS, 2) dense_simt_kernel(
     // rows in flight per warp: four when the queries leave registers for it (latency mode: the kernel is
     // purely HBM-bound and needs ~64 KB of loads outstanding per SM), else two.  (A rolling window that issues a
     // row's loads three rows ahead of its scoring, with L1::no_allocate loads, measured SLOWER: 4.06 vs 2.79 ms
-    // at 10 M x 768 -- the batch of twelve 16-byte loads per warp is what keeps HBM busy.)
+    // at 10 M x 768 -- the batch of twelve 16-byte loads per warp is what keeps HBM busy.  L1::no_allocate /
+    // L2::evict_first loads in THIS loop: 2.786 vs 2.786 ms, no difference.)
     int64_t r = r_begin + warp;
     if (QT <= 2) {
       for (; r + 3 * SIMT_WARPS < r_end; r += 4 * SIMT_WARPS) {
