@@ -30,6 +30,17 @@ class Bm25IndexStruct(C.Structure):
                 ("impacts_nonneg", C.c_int32)]
 
 
+class SingleChars(C.Structure):
+    """``drs_single_chars``: bit c set = the one-character token chr(c) is kept."""
+    _fields_ = [("bits", C.c_uint32 * 8)]
+
+
+class VocabTableStruct(C.Structure):
+    """``drs_vocab_table`` (include/drs_b200.h)."""
+    _fields_ = [("d_slot_hash", _vp), ("d_slot_term", _vp), ("d_str_offsets", _vp), ("d_pool", _vp),
+                ("capacity", _i64), ("n_slots", _i64)]
+
+
 EXPORTS = {
     "drs_version": (C.c_int, []),
     "drs_last_error": (C.c_char_p, []),
@@ -52,6 +63,8 @@ EXPORTS = {
     "drs_candidate_cosines": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "drs_merge_gathered": (C.c_int, [_vp, _i32, _sz, _sz, _i32, _sz, _sz, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "drs_rerank_from_cosines": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "drs_tokenize_count": (C.c_int, [_vp, _vp, _i32, C.POINTER(SingleChars), _vp, _vp]),
+    "drs_tokenize_lookup": (C.c_int, [_vp, _vp, _i32, C.POINTER(SingleChars), C.POINTER(VocabTableStruct), _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -192,6 +205,26 @@ def bm25_topk(index_struct: Bm25IndexStruct, q_terms, q_offsets, n_queries, kpri
                                     BM25_MODES[mode], _ptr(scores), _ptr(ids), _ptr(flags) if want_flags else None,
                                     _ptr(buf), buf.numel(), _stream()))
     return (scores, ids, flags) if want_flags else (scores, ids)
+
+
+def tokenize_lookup(text: torch.Tensor, text_offsets: torch.Tensor, keep1: SingleChars, table: VocabTableStruct):
+    """ASCII query strings (uint8 bytes back to back + int64 offsets, device tensors) -> (q_terms int32, q_offsets
+    int32 [Q+1]) on the device, the pair ``bm25_topk`` reads: the reference tokeniser + vocabulary lookup."""
+    _need_cuda(text_offsets)
+    lib = load()
+    dev = text_offsets.device
+    n = text_offsets.numel() - 1
+    counts = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.drs_tokenize_count(_ptr(text), _ptr(text_offsets), n, C.byref(keep1), _ptr(counts), _stream()))
+        offsets = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        if n:
+            offsets[1:] = torch.cumsum(counts[:n], 0)
+        total = int(offsets[-1].item()) if n else 0
+        terms = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        _check(lib.drs_tokenize_lookup(_ptr(text), _ptr(text_offsets), n, C.byref(keep1), C.byref(table), _ptr(offsets),
+                                       _ptr(terms), _stream()))
+    return terms[:total], offsets
 
 
 def fuse_topk(mode, v_scores, v_ids, b_scores, b_ids, top_k, fusion_key=None, rrf_k=60.0, w_vector=0.5, w_bm25=0.5,

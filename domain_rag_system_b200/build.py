@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdrs_b200.so")
-SOURCES = ["api.cu", "select.cu", "dense_simt.cu", "dense_umma.cu", "dense_pair.cu", "bm25.cu", "fuse.cu", "rerank.cu", "shard.cu"]
+SOURCES = ["api.cu", "select.cu", "dense_simt.cu", "dense_umma.cu", "dense_pair.cu", "bm25.cu", "fuse.cu", "rerank.cu", "shard.cu", "tokenize.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 

@@ -19,7 +19,7 @@ build) and on the CPU in unit tests; only the V-long idf loop is Python.
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -57,6 +57,7 @@ class Bm25DeviceIndex:
         self.avgdl = 0.0
         self.average_idf = 0.0
         self.vocab: Dict[str, int] | None = None   # term string -> id (None for id-only corpora)
+        self._vtab = None                          # device lookup table over the vocabulary (encode_texts)
         self.vocab_present = 0                     # number of distinct terms that occur
         self.row_offset = 0                        # global row of local document 0 (sharded corpora)
         self.n_docs_global = 0
@@ -309,6 +310,95 @@ class Bm25DeviceIndex:
         if pinned:
             qt, qo = qt.pin_memory(), qo.pin_memory()
         return qt, qo
+
+    # -- query strings -> term ids on the device --------------------------------
+    @staticmethod
+    def vocab_table_arrays(words: Sequence[Optional[str]]):
+        """Host arrays of the device lookup table over ``words[term_id]`` (None = id without a string): 64-bit
+        FNV-1a of every string (vectorised over character positions), entries placed in order of their home slot
+        with no wrap-around (``pos_i = max(home_i, pos_{i-1} + 1)``), so a probe walks forward from the home slot
+        to the first empty one.  Returns (slot_hash uint64 [n_slots], slot_term int32 [n_slots], str_offsets int64
+        [V+1], pool uint8, capacity)."""
+        v = len(words)
+        enc = [w.encode("utf-8") if w else b"" for w in words]
+        lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=v)
+        offs = np.zeros(v + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        pool = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if offs[-1] else np.zeros(1, dtype=np.uint8)
+        h = np.full(v, 0xCBF29CE484222325, dtype=np.uint64)
+        prime = np.uint64(0x100000001B3)
+        for pos in range(int(lens.max()) if v else 0):
+            m = lens > pos
+            h[m] = (h[m] ^ pool[offs[:-1][m] + pos].astype(np.uint64)) * prime
+        ids = np.flatnonzero(lens > 0)
+        n = ids.size
+        cap = 16
+        while cap < 2 * max(n, 1):
+            cap *= 2
+        home = (h[ids] & np.uint64(cap - 1)).astype(np.int64)
+        order = np.argsort(home, kind="stable")
+        ar = np.arange(n, dtype=np.int64)
+        pos = np.maximum.accumulate(home[order] - ar) + ar if n else ar
+        n_slots = cap + n + 1
+        slot_hash = np.zeros(n_slots, dtype=np.uint64)
+        slot_term = np.full(n_slots, -1, dtype=np.int32)
+        slot_hash[pos] = h[ids][order]
+        slot_term[pos] = ids[order].astype(np.int32)
+        return slot_hash, slot_term, offs, pool, cap
+
+    def _vocab_table(self):
+        """The device copy of ``vocab_table_arrays`` for this index's vocabulary (built once, on first use)."""
+        if self._vtab is None:
+            words: List[Optional[str]] = [None] * self.n_terms
+            for w, t in (self.vocab or {}).items():
+                if 0 <= t < self.n_terms:
+                    words[t] = w
+            sh, st, offs, pool, cap = self.vocab_table_arrays(words)
+            dev = self.t["post_doc"].device
+            keep = {"sh": torch.from_numpy(sh.view(np.int64)).to(dev), "st": torch.from_numpy(st).to(dev),
+                    "offs": torch.from_numpy(offs).to(dev), "pool": torch.from_numpy(pool).to(dev)}
+            s = _lib.VocabTableStruct()
+            s.d_slot_hash, s.d_slot_term = keep["sh"].data_ptr(), keep["st"].data_ptr()
+            s.d_str_offsets, s.d_pool = keep["offs"].data_ptr(), keep["pool"].data_ptr()
+            s.capacity, s.n_slots = (cap if self.vocab else 0), sh.size
+            self._vtab = (s, keep)
+        return self._vtab[0]
+
+    def encode_texts(self, texts: Sequence[str], keep_single: Sequence[str] = (), host_tokenize=None):
+        """Query STRINGS -> (q_terms int32, q_offsets int32 [Q+1]) DEVICE tensors: the reference's tokeniser
+        (``BM25Indexer.tokenize``, src/indexing/bm25_indexer.py:50-78) and vocabulary lookup run on the GPU
+        (``drs_tokenize_lookup``), one launch pair for the whole batch, no Python work per token.
+        ``keep_single``: the lower-cased abbreviation keys of one character (the only one-character tokens the
+        reference keeps).  ASCII strings are exact on the device; a string with non-ASCII characters (Unicode
+        ``lower()`` / ``\\w``) goes through ``host_tokenize`` + the vocabulary dict and is spliced in."""
+        dev = self.t["post_doc"].device
+        ok = [t.isascii() for t in texts]
+        enc = [t.encode("ascii") if a else b"" for t, a in zip(texts, ok)]
+        offs = np.zeros(len(texts) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        raw = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if offs[-1] else np.zeros(1, dtype=np.uint8)
+        keep1 = _lib.SingleChars()
+        for c in keep_single:
+            if len(c) == 1 and c.isascii():
+                keep1.bits[ord(c) >> 5] |= 1 << (ord(c) & 31)
+        terms, q_offs = _lib.tokenize_lookup(torch.from_numpy(raw).to(dev), torch.from_numpy(offs).to(dev), keep1,
+                                             self._vocab_table())
+        if all(ok):
+            return terms, q_offs
+        if host_tokenize is None:
+            raise ValueError("encode_texts: non-ASCII query text needs host_tokenize")
+        # rare path: splice the host-tokenised strings into the device result
+        t_h, o_h = terms.cpu().numpy(), q_offs.cpu().numpy()
+        parts = []
+        for i, a in enumerate(ok):
+            if a:
+                parts.append(t_h[o_h[i]:o_h[i + 1]])
+            else:
+                parts.append(self.encode_queries([host_tokenize(texts[i])])[0].numpy())
+        qo = np.zeros(len(texts) + 1, dtype=np.int32)
+        np.cumsum([len(x) for x in parts], out=qo[1:])
+        qt = np.concatenate(parts).astype(np.int32) if qo[-1] else np.zeros(0, dtype=np.int32)
+        return torch.from_numpy(qt).to(dev), torch.from_numpy(qo).to(dev)
 
     # -- wide windows ---------------------------------------------------------------------------
     def exact_scores(self, term_ids) -> torch.Tensor:

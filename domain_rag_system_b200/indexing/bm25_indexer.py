@@ -83,6 +83,13 @@ class BM25Indexer:
         preserved = [a.lower() for a in self.normalizer.abbreviations.keys() if a.lower() in text]
         return [t for t in _TOKEN.findall(text) if len(t) >= 2 or t in preserved]
 
+    def encode_texts(self, texts):
+        """Batch of query strings -> (q_terms, q_offsets) device tensors: ``tokenize`` + the vocabulary lookup on the
+        GPU for ASCII strings (exactly the host tokeniser's tokens), the host tokeniser for the others."""
+        keys = {a.lower() for a in self.normalizer.abbreviations.keys()}
+        return self.bm25.encode_texts(list(texts), keep_single=[k for k in keys if len(k) == 1],
+                                      host_tokenize=self.tokenize)
+
     # -- bm25_indexer.py:80-111 --------------------------------------------------------
     def index_chunks(self, chunks: List):
         print(f"\nIndexing {len(chunks)} chunks with BM25...")

@@ -197,8 +197,11 @@ class HybridIndexer:
         if vi is not None:
             qv = torch.from_numpy(np.ascontiguousarray(np.asarray(vi.embedder.encode(list(queries)), dtype=np.float32))).to(dev)
         if bi is not None:
-            qt, qo = bi.bm25.encode_queries([bi.tokenize(q) for q in queries])
-            qt, qo = qt.to(dev), qo.to(dev)
+            if bi.bm25.vocab is not None:
+                qt, qo = bi.encode_texts(queries)            # tokeniser + vocabulary lookup on the device
+            else:
+                qt, qo = bi.bm25.encode_queries([bi.tokenize(q) for q in queries])
+                qt, qo = qt.to(dev), qo.to(dev)
         else:
             qt = qo = None
         nq = len(queries)

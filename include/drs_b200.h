@@ -230,6 +230,42 @@ int drs_rerank_from_cosines(const int64_t* d_pool_ids, int n_queries, int top_n,
                             const float* d_v_cos, int kv, const int64_t* d_b_ids, const float* d_b_cos, int kb,
                             float* d_out_scores, int64_t* d_out_ids, int32_t* d_out_pos, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Query tokenisation + vocabulary lookup for a batch of ASCII query strings.
+ * Replaces BM25Indexer.tokenize (src/indexing/bm25_indexer.py:50-78: text.lower(), re.findall(r'\b\w+\b'),
+ * one-character tokens kept only when they are abbreviation keys) and the per-token dictionary lookups of
+ * rank_bm25.BM25Okapi.get_scores as called from BM25Indexer.search (src/indexing/bm25_indexer.py:125-127).
+ * For ASCII bytes those semantics are byte-level and reproduced exactly; strings with any byte >= 0x80 must be
+ * tokenised by the caller (Unicode-defined lower() / \w) -- pass them as empty strings here.
+ *
+ * d_text: the strings' UTF-8 bytes back to back; d_text_offsets int64 [n_texts + 1].
+ * drs_single_chars: bit c set = the one-character token c (lower case) is kept.
+ * drs_vocab_table: open addressing keyed by 64-bit FNV-1a (offset basis 0xcbf29ce484222325, prime 0x100000001b3) of
+ *   the lower-cased token; home slot = hash & (capacity - 1), capacity a power of two; entries sit at or after their
+ *   home slot in home-slot order WITHOUT wrap-around (n_slots >= capacity + number of entries), empty slots hold
+ *   term -1.  d_str_offsets int64 [V + 1] / d_pool: the vocabulary strings by term id, used to confirm a hash match
+ *   byte by byte (the lookup is exact).  capacity 0 = no vocabulary (every token maps to -1).
+ * drs_tokenize_count: d_counts[q] = tokens of text q.  drs_tokenize_lookup: term ids (or -1: out of vocabulary,
+ *   which drs_bm25_topk skips like rank_bm25 does) written at d_out_terms[d_out_offsets[q] ..), d_out_offsets being
+ *   the exclusive prefix sum of the counts -- i.e. the (q_terms, q_offsets) pair drs_bm25_topk reads.
+ * ------------------------------------------------------------------------------- */
+typedef struct drs_single_chars {
+  uint32_t bits[8];
+} drs_single_chars;
+typedef struct drs_vocab_table {
+  const uint64_t* d_slot_hash;   /* [n_slots] */
+  const int32_t* d_slot_term;    /* [n_slots] term id or -1 */
+  const int64_t* d_str_offsets;  /* [V + 1] */
+  const uint8_t* d_pool;         /* vocabulary strings (lower case), term id order */
+  int64_t capacity;              /* power of two, or 0 */
+  int64_t n_slots;
+} drs_vocab_table;
+int drs_tokenize_count(const uint8_t* d_text, const int64_t* d_text_offsets, int n_texts,
+                       const drs_single_chars* keep1, int32_t* d_counts, void* stream);
+int drs_tokenize_lookup(const uint8_t* d_text, const int64_t* d_text_offsets, int n_texts,
+                        const drs_single_chars* keep1, const drs_vocab_table* table, const int32_t* d_out_offsets,
+                        int32_t* d_out_terms, void* stream);
+
 /* Which kernel the last drs_dense_topk call on this thread used: DRS_DENSE_SIMT (1), DRS_DENSE_UMMA (2, the
  * single-CTA tensor kernel) or 3 (the CTA-pair tensor kernel). */
 int drs_dense_last_kernel(void);

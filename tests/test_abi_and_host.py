@@ -333,3 +333,79 @@ def test_built_objects_contain_blackwell_native_instructions():
         for n in needles:
             assert n in sass, f"{obj}: no {n} in SASS"
         assert " HMMA" not in sass and "HGMMA" not in sass, f"{obj}: legacy tensor-core path present"
+
+
+# ---- device tokeniser (csrc/tokenize.cu): CPU models of what the kernel does ---------------------------------------
+def _ascii_tokens_model(text: str, keep1=()):
+    """Byte-level restatement of tokenize_kernel: maximal runs of [A-Za-z0-9_], lower-cased, one-character runs kept
+    only when listed."""
+    out, cur = [], []
+    for ch in text + " ":
+        if ch.isascii() and (ch.isalnum() or ch == "_"):
+            cur.append(ch.lower())
+        elif cur:
+            tok = "".join(cur)
+            if len(tok) >= 2 or tok in keep1:
+                out.append(tok)
+            cur = []
+    return out
+
+
+def test_ascii_tokeniser_model_equals_the_reference_style_tokeniser():
+    """For ASCII text the reference tokeniser (lower(), \\b\\w+\\b, one-character tokens only when they are abbreviation
+    keys; reproduced by BM25Indexer.tokenize, which the golden test pins) is byte-level: the model the CUDA kernel
+    implements yields the same tokens."""
+    from domain_rag_system_b200.indexing.bm25_indexer import BM25Indexer
+
+    class Norm:
+        abbreviations = {"K": "potassium", "MI": "myocardial infarction", "x": "times", "IV": "intravenous"}
+
+    bi = BM25Indexer.__new__(BM25Indexer)         # tokenize() only reads .normalizer
+    bi.normalizer = Norm()
+    keep1 = {a.lower() for a in Norm.abbreviations if len(a.lower()) == 1}
+    rng = np.random.default_rng(11)
+    alphabet = list("abcXYZ019_ -.,;:/()[]'\"\t\n!?%+k")
+    texts = ["", " ", "a", "K", "k+ 5 mmol/L", "Patient_1 has MI; IV fluids x 2 (BP 120/80).", "__init__ __", "a_b-c_d",
+             "3.5mg/kg  q8h", "x" * 300, "END."]
+    texts += ["".join(rng.choice(alphabet, size=int(rng.integers(0, 60)))) for _ in range(300)]
+    for t in texts:
+        assert _ascii_tokens_model(t, keep1) == bi.tokenize(t), repr(t)
+
+
+def test_vocab_table_layout_finds_every_word_and_only_those():
+    """Bm25DeviceIndex.vocab_table_arrays: replay the kernel's probe (home slot forward to the first empty slot, hash
+    then bytes) on the host arrays."""
+    rng = np.random.default_rng(5)
+    words = [None if i % 17 == 3 else "w%05d" % i for i in range(3000)]
+    words += ["".join(rng.choice(list("abcdefgh"), size=int(rng.integers(1, 9)))) + "_%d" % i for i in range(500)]
+    words += ["naïve", "µg"]                                    # non-ASCII vocabulary entries: present, never matched by ASCII
+    sh, st, offs, pool, cap = Bm25DeviceIndex.vocab_table_arrays(words)
+    assert cap & (cap - 1) == 0 and sh.size == st.size and sh.size >= cap + sum(w is not None for w in words)
+    mask64 = (1 << 64) - 1
+
+    def fnv(b):
+        h = 0xCBF29CE484222325
+        for c in b:
+            h = ((h ^ c) * 0x100000001B3) & mask64
+        return h
+
+    def lookup(tok: bytes):
+        h = fnv(tok)
+        s = h & (cap - 1)
+        while s < sh.size:
+            t = int(st[s])
+            if t < 0:
+                return -1
+            if int(sh[s]) == h and bytes(pool[offs[t]:offs[t + 1]]) == tok:
+                return t
+            s += 1
+        return -1
+
+    for i, w in enumerate(words):
+        if w is not None:
+            assert lookup(w.encode("utf-8")) == i
+    for miss in (b"", b"w99999", b"zzz", b"W00001", b"w0000"):
+        assert lookup(miss) == -1
+    # an empty vocabulary is a table that answers -1
+    sh0, st0, _, _, cap0 = Bm25DeviceIndex.vocab_table_arrays([])
+    assert (st0 == -1).all() and cap0 >= 16

@@ -796,3 +796,38 @@ def test_search_many_equals_the_per_query_loop(tmp_path):
         for qtext, got in zip(qtexts, many):
             want = rr.rerank(qtext, hi.search(qtext, top_k=10, fusion_method=method, **kw), top_k=5)
             assert got == want
+
+
+@pytest.mark.gpu
+def test_device_tokeniser_and_vocabulary_lookup_equal_the_host_path(tmp_path):
+    """drs_tokenize_count / drs_tokenize_lookup: for a batch of query strings the device returns exactly
+    the (q_terms, q_offsets) the host path builds from BM25Indexer.tokenize + the vocabulary dict -- ASCII strings on
+    the GPU, strings with non-ASCII characters spliced in from the host tokeniser."""
+    g, chunks, te, qtexts, _ = _filters_setup(tmp_path)
+
+    class Norm:
+        abbreviations = {"K": "potassium", "MI": "myocardial infarction", "x": "times"}
+
+    bi = BM25Indexer(medical_normalizer=Norm())
+    bi.index_chunks(chunks)
+    vocab_words = list(bi.bm25.vocab)[:50]
+    texts = list(qtexts) + [
+        "", "   ", "?!", "a", "K", "k x 5", " ".join(vocab_words), " ".join(w.upper() for w in vocab_words[:20]),
+        ",".join(vocab_words[:10]) + ";;unknownword_123 zzzz", vocab_words[0] + "_" + vocab_words[1], "x" * 500,
+        "naïve µg " + vocab_words[3], vocab_words[4] + " café", "\t" + vocab_words[5] + "\n" + vocab_words[6] + ".",
+    ]
+    want_t, want_o = bi.bm25.encode_queries([bi.tokenize(t) for t in texts])
+    got_t, got_o = bi.encode_texts(texts)
+    assert got_t.is_cuda and got_o.is_cuda
+    assert got_o.cpu().tolist() == want_o.tolist()
+    assert got_t.cpu().tolist() == want_t.tolist()
+    assert (want_t >= 0).sum() > 100 and (want_t < 0).sum() > 3          # the case has hits and misses
+    # and the searches that follow are the same
+    a = bi.topk_terms(got_t, got_o, len(texts), 10)
+    b = bi.topk_terms(want_t.cuda(), want_o.cuda(), len(texts), 10)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # an index over term ids has no vocabulary: every token is out of vocabulary
+    offs, toks = synth.zipf_docs(500, vocab=100, seed=3)
+    ix = Bm25DeviceIndex.from_token_ids(offs, toks, 100, device="cuda")
+    t, o = ix.encode_texts(["w00001 w00002", ""])
+    assert o.cpu().tolist() == [0, 2, 2] and t.cpu().tolist() == [-1, -1]
