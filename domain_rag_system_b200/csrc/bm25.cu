@@ -685,6 +685,8 @@ __global__ void __launch_bounds__(BM25_THREADS, CPS) bm25_select_kernel(
           const int cnt_now = cnt_list + s_note[par];   // the accumulation ended with a barrier
           if (cnt_now <= cap) {        // (else: more crossings than the append area holds -- scan the ordinary way)
             if (cnt_now > cnt_list) {  // noted documents -> keys, with their FINAL scores
+              // (Letting every thread convert the notes of the documents it owns in pass A -- which needs no barrier
+              // before the next tile -- was measured SLOWER, 1.335 vs 1.303 ms: the barrier keeps the warps in phase.)
               for (int i = cnt_list + tid; i < cnt_now; i += BM25_THREADS) {
                 const int dl = int(mbuf[kk + i]);
                 const uint64_t key = make_key_fx(sc[dl], uint32_t(doc0 + dl));
