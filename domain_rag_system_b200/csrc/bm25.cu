@@ -10,10 +10,11 @@
 //   * per (tile, query), on an int32 score tile in shared memory:
 //       pass A -- the query's head terms (df >= N/4: ~94 % of a Zipfian query's postings) are added from dense
 //                 rows of packed 14-bit values (16-byte loads = 8 documents, four rows summed as packed 16-bit
-//                 lanes), by the thread that owns the documents; the first sweep also initialises the tile;
+//                 lanes), by the thread that owns the documents; the first sweep also initialises the tile
+//                 (bm25_dense_sweep, specialised on the number of rows);
 //       pass B -- the other terms' postings inside the tile are cut into chunks of 128 (aligned 16-byte loads of
-//                 doc ids and impacts), the warps take chunks round-robin with the next chunk's loads in flight,
-//                 and add with shared-memory integer atomics;
+//                 doc ids and impacts), the warps take chunks round-robin over two register sets with the next
+//                 chunk's loads in flight, and add with shared-memory integer atomics;
 //       selection -- with a warm positive threshold and no negative impacts, sums only grow: the thread that
 //                 takes a document across the threshold (old < tau <= new) notes it, and the tile is never
 //                 scanned.  Otherwise (cold list, negative-idf corpora): a vectorised scan, highest document
@@ -27,8 +28,11 @@
 // top-k' of a flagged query is re-scored exactly; exact (score, doc) top-k' per slice, merged by merge_pairs.
 //
 // The kernel's algorithmic traffic is 8 bytes per posting visited; real DRAM traffic is ~100x lower
-// (2-byte head-term rows shared by all queries through L2), so its practical bound is issue slots, shared-memory
-// atomics and the per-phase latency of every (tile, query) pair, not HBM.
+// (2-byte head-term rows shared by all queries through L2).  What bounds it (profiles/r2t_summary.txt): the
+// dependent chain of a (tile, query) pass -- rows, barrier, postings, barrier, selection; ~11.4 k cycles per tile,
+// four passes in flight per SM -- with the SM saturated by the mix (issue slots 56 %, LSU 56 %), no unit at its peak.
+// DRS_BM25_TRACE prints the phase timeline of one CTA, DRS_BM25_DEBUG switches phases off for timing experiments,
+// DRS_BM25_CTAS=5 selects the 48-register build (five CTAs per SM).
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
