@@ -29,6 +29,26 @@ def main():
     qv, q_terms, q_offs = qv.to(dev), q_terms.to(dev), q_offs.to(dev)
     s = ShardedHybridSearcher(rows, inv, ix, 0, world=1)
     kw = dict(top_k=50, fusion_method="weighted", rerank_top_n=50, final_k=10)
+    ref = None
+    for v in os.environ.get("STREAM_AB", "").split(","):      # STREAM_AB=0,3,4,6: 0 = load-then-score kernel, n = ring stages
+        if v == "":
+            continue
+        os.environ["DRS_DENSE_STREAM"] = "0" if v == "0" else "1"
+        os.environ["DRS_STREAM_STAGES"] = v if v != "0" else "3"
+        for _ in range(3):
+            out = s.search_batch(qv, q_terms, q_offs, **kw)
+        torch.cuda.synchronize()
+        same = None if ref is None else bool(torch.equal(ref[0], out[0]) and torch.equal(ref[1], out[1]))
+        ref = ref or (out[0].clone(), out[1].clone())
+        _lib.profile_enable(True)
+        for _ in range(50):
+            s.search_batch(qv, q_terms, q_offs, **kw)
+        pr = _lib.profile_read()
+        _lib.profile_enable(False)
+        print(json.dumps({"dense_stream": v, "dense_select_ms": round(pr["dense_select"][0] / pr["dense_select"][1], 4),
+                          "same_result_as_first": same}))
+    os.environ.pop("DRS_DENSE_STREAM", None)
+    os.environ.pop("DRS_STREAM_STAGES", None)
     for _ in range(5):
         s.search_batch(qv, q_terms, q_offs, **kw)
     torch.cuda.synchronize()
