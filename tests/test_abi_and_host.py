@@ -327,7 +327,8 @@ def test_built_objects_contain_blackwell_native_instructions():
         pytest.skip("cuobjdump not available")
     _build.build()
     want = {"dense_pair.o": ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "LDTM", "UTCBAR.2CTA.MULTICAST"),
-            "dense_umma.o": ("UTCHMMA", "UTMALDG.2D", "LDTM", "STTM")}
+            "dense_umma.o": ("UTCHMMA", "UTMALDG.2D", "LDTM", "STTM"),
+            "dense_simt.o": ("UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK.TRANS64.TRYWAIT")}   # bulk-copy ring
     for obj, needles in want.items():
         sass = subprocess.run([cuobjdump, "-sass", os.path.join(_build.CSRC, obj)], capture_output=True, text=True).stdout
         for n in needles:
