@@ -86,3 +86,67 @@ def test_plan_rule_matches_the_model():
         for ni in (2, 3):
             trimmed = (ns // ni) * ni
             assert trimmed % ni == 0 and 0 < trimmed <= ns
+
+
+def simulate_stream_ring(n_stages, n_consumers, n_chunks, seed):
+    """dense_stream_kernel (csrc/dense_simt.cu): ONE producer lane, n_consumers warps that each read EVERY chunk.
+    full[s] completes when the bulk copy of the chunk has landed (one arrive.expect_tx + the copy's bytes); empty[s]
+    completes when all n_consumers warps have arrived.  Producer: waits empty[s] with parity ((c / S) - 1) & 1 for
+    c >= S only (the first lap finds the ring empty).  Consumer: waits full[s] with parity (c / S) & 1.
+    A violation = a consumer reads a slot that does not hold its chunk, or the producer overwrites a slot some warp
+    has not finished reading."""
+    rng = random.Random(seed)
+    full_phase = [0] * n_stages
+    empty_phase = [0] * n_stages
+    empty_arrivals = [0] * n_stages
+    content = [None] * n_stages
+    readers_done = [n_consumers] * n_stages          # warps that finished the slot's current content
+    events = []
+    prod_c = 0
+    cons_c = [0] * n_consumers
+    busy_until = [0] * n_consumers
+    violations, t = 0, 0
+    while min(cons_c) < n_chunks and t < 400_000:
+        t += 1
+        for ev in [e for e in events if e[0] <= t]:
+            events.remove(ev)
+            _, kind, slot, chunk, w = ev
+            if kind == "landed":
+                content[slot] = chunk
+                readers_done[slot] = 0
+                full_phase[slot] += 1
+            else:                                         # a warp finished reading: arrives on empty[slot]
+                readers_done[slot] += 1
+                empty_arrivals[slot] += 1
+                if empty_arrivals[slot] == n_consumers:
+                    empty_arrivals[slot] = 0
+                    empty_phase[slot] += 1
+        if prod_c < n_chunks:
+            s, lap = prod_c % n_stages, prod_c // n_stages
+            ok = True if prod_c < n_stages else ((empty_phase[s] & 1) != ((lap - 1) & 1))
+            if ok:
+                if readers_done[s] != n_consumers:
+                    violations += 1                       # overwriting a slot that is still being read
+                content[s] = None
+                events.append((t + rng.randint(50, 600), "landed", s, prod_c, -1))
+                prod_c += 1
+        for w in range(n_consumers):
+            c = cons_c[w]
+            if c >= n_chunks or busy_until[w] > t:
+                continue
+            s, lap = c % n_stages, c // n_stages
+            if (full_phase[s] & 1) != (lap & 1):          # try_wait.parity(lap & 1) succeeded
+                if content[s] != c:
+                    violations += 1
+                d = rng.randint(20, 300)
+                busy_until[w] = t + d
+                events.append((t + d, "read_done", s, c, w))
+                cons_c[w] = c + 1
+    return violations, min(cons_c)
+
+
+@pytest.mark.parametrize("n_stages", [2, 3, 4, 8])
+def test_stream_ring_never_reads_stale_or_overwrites_live_slots(n_stages):
+    for seed in range(4):
+        violations, done = simulate_stream_ring(n_stages, 8, 60, seed)
+        assert violations == 0 and done == 60
